@@ -1,0 +1,798 @@
+// libkfb200.so — context, stage drivers and the C ABI declared in include/kfb200.h.
+// Host-side control flow follows the reference's stage drivers
+// (kfusion/src/cpp/kernels.cpp:915-1055); all per-pixel / per-voxel work is in
+// kfb_kernels.cuh.  There is NO CPU fallback: every entry point that computes needs a
+// CUDA device and fails with an error code otherwise.
+#include "../../include/kfb200.h"
+#include "kfb_kernels.cuh"
+
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+// constant_parameters.h:15-23
+static const float c_e_delta = 0.1f;
+static const int c_radius = 2;
+static const float c_dist_threshold = 0.1f;
+static const float c_normal_threshold = 0.8f;
+static const float c_track_threshold = 0.15f;
+static const float c_maxweight = 100.0f;
+static const float c_nearPlane = 0.4f;
+static const float c_farPlane = 4.0f;
+static const float c_delta = 4.0f;
+
+static thread_local char g_err[512] = "";
+static int set_err(int code, const char* fmt, ...) {
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof g_err, fmt, ap);
+	va_end(ap);
+	return code;
+}
+#define KFB_E_CUDA 2
+#define KFB_E_ARG 3
+#define KFB_E_STATE 4
+#define CK(call)                                                                                             \
+	do {                                                                                                     \
+		cudaError_t e_ = (call);                                                                             \
+		if (e_ != cudaSuccess) return set_err(KFB_E_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+	} while (0)
+
+#define NUPD_SLOTS 4096
+
+struct EvPair { cudaEvent_t a, b; };
+struct StageTimer {
+	std::vector<EvPair> pending, pool;
+	double total_ms = 0;
+	float last_ms = 0;
+	uint64_t count = 0;
+};
+
+struct kfb_ctx {
+	kfb_config cfg;
+	int device;
+	cudaStream_t stream;
+	uint32_t cw, ch;
+	int levels;
+	uint32_t lw[KFB_MAX_LEVELS], lh[KFB_MAX_LEVELS];
+	float step;
+	// host pose state (the reference's `pose` member and oldPose / raycastPose globals)
+	float pose[16], oldPose[16], raycastPose[16];
+	float reduction[32];
+	float gaussian[5];
+	// device buffers
+	short2* d_vol;
+	uint32_t z0, z1;            // slab
+	size_t slab_voxels;
+	float *d_vertex, *d_normal; // raycast maps
+	float* d_floatDepth;
+	float* d_scaled[KFB_MAX_LEVELS];
+	float* d_inV[KFB_MAX_LEVELS];
+	float* d_inN[KFB_MAX_LEVELS];
+	uint16_t* d_input; size_t input_bytes;
+	uint16_t* h_stage; size_t stage_bytes;
+	int8_t* d_status;
+	double* d_partials;
+	unsigned int* d_counter;
+	float* d_out32;
+	float* h_out32;             // mapped pinned: [0..31] result, [32] seq flag
+	float* h_out32_dev;
+	uint32_t seq;
+	unsigned long long* d_nupd; // NUPD_SLOTS per-integrate counters
+	uint64_t integrate_count;
+	uchar4* d_render; size_t render_bytes;
+	// multi-GPU
+	int rank, world;
+	VolView view_all;           // slab table for raycast
+	void* peer_ptrs[KFB_MAX_SLABS];
+	void* nccl_comm;
+	// registered host pointers (benchmark.cpp reuses one malloc'd frame buffer)
+	const void* reg_ptr[4]; size_t reg_bytes[4]; int n_reg;
+	// stats
+	kfb_stats st;
+	bool timing;
+	StageTimer t_pre, t_track, t_int, t_ray;
+};
+
+// ------------------------------------------------------------------------------------------
+static void timer_begin(kfb_ctx* c, StageTimer& t) {
+	if (!c->timing) return;
+	EvPair p;
+	if (!t.pool.empty()) { p = t.pool.back(); t.pool.pop_back(); }
+	else { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
+	cudaEventRecord(p.a, c->stream);
+	t.pending.push_back(p);
+}
+static void timer_end(kfb_ctx* c, StageTimer& t) {
+	if (!c->timing) return;
+	cudaEventRecord(t.pending.back().b, c->stream);
+}
+static void timer_resolve(kfb_ctx* c, StageTimer& t) {
+	for (auto& p : t.pending) {
+		cudaEventSynchronize(p.b);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, p.a, p.b);
+		t.total_ms += ms; t.last_ms = ms; t.count++;
+		t.pool.push_back(p);
+	}
+	t.pending.clear();
+}
+static void timer_free(StageTimer& t) {
+	for (auto& p : t.pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+	for (auto& p : t.pool) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+	t.pending.clear(); t.pool.clear();
+}
+
+static inline Mat4 toMat(const float* m) { Mat4 r; memcpy(r.m, m, sizeof r.m); return r; }
+#define LAUNCHED(c) ((c)->st.kernel_launches++)
+
+static int launch_init_volume(kfb_ctx* c) {
+	const size_t n = c->slab_voxels, n4 = n / 4;
+	k_init_volume<<<148 * 8, 256, 0, c->stream>>>((uint4*) c->d_vol, n4, c->d_vol, n);
+	LAUNCHED(c);
+	CK(cudaGetLastError());
+	return 0;
+}
+
+extern "C" {
+
+int kfb_abi_version(void) { return KFB_ABI_VERSION; }
+const char* kfb_last_error(void) { return g_err; }
+
+void kfb_inverse4(float out[16], const float in[16]) { hm_inverse4(out, in); }
+void kfb_matmul4(float out[16], const float a[16], const float b[16]) { hm_matmul4(out, a, b); }
+void kfb_camera_matrix(float out[16], const float k[4]) { hm_camera_matrix(out, k); }
+void kfb_inverse_camera_matrix(float out[16], const float k[4]) { hm_inverse_camera_matrix(out, k); }
+int kfb_k_update_pose(float pose[16], const float red[32], float icp_threshold, int* converged) {
+	const int r = hm_update_pose(pose, red, icp_threshold);
+	if (converged) *converged = r;
+	return 0;
+}
+int kfb_k_check_pose(float pose[16], const float old_pose[16], const float red[32], uint32_t w, uint32_t h, float thr, int* ok) {
+	const int r = hm_check_pose(pose, old_pose, red, w, h, thr);
+	if (ok) *ok = r;
+	return 0;
+}
+
+int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
+	if (!cfg || !out) return set_err(KFB_E_ARG, "null argument");
+	if (cfg->n_levels < 1 || cfg->n_levels > 3)
+		return set_err(KFB_E_ARG, "pyramid levels must be 1..3 (got %d)", cfg->n_levels);
+	if (cfg->compute_w == 0 || cfg->compute_h == 0 || cfg->volume_res[0] == 0 || cfg->volume_res[1] == 0 || cfg->volume_res[2] == 0)
+		return set_err(KFB_E_ARG, "empty image or volume");
+	if ((cfg->compute_w >> (cfg->n_levels - 1)) == 0 || (cfg->compute_h >> (cfg->n_levels - 1)) == 0)
+		return set_err(KFB_E_ARG, "image too small for %d pyramid levels", cfg->n_levels);
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return set_err(KFB_E_CUDA, "no CUDA device: libkfb200 has no CPU fallback");
+	if (cfg->device < 0 || cfg->device >= ndev) return set_err(KFB_E_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+	CK(cudaSetDevice(cfg->device));
+	kfb_ctx* c = new kfb_ctx();
+	memset(&c->st, 0, sizeof c->st);
+	c->cfg = *cfg;
+	c->device = cfg->device;
+	c->cw = cfg->compute_w; c->ch = cfg->compute_h;
+	c->levels = cfg->n_levels;
+	for (int l = 0; l < c->levels; ++l) { c->lw[l] = c->cw >> l; c->lh[l] = c->ch >> l; }
+	memcpy(c->pose, cfg->init_pose, sizeof c->pose);
+	memset(c->oldPose, 0, sizeof c->oldPose);        // zero-initialised globals (cpp/kernels.cpp:52-53)
+	memset(c->raycastPose, 0, sizeof c->raycastPose);
+	memset(c->reduction, 0, sizeof c->reduction);    // calloc'd (cpp/kernels.cpp:73)
+	// step = min(volumeDimensions) / max(volumeResolution)   kernels.h:116
+	{
+		const float mind = kminf(kminf(cfg->volume_dim[0], cfg->volume_dim[1]), cfg->volume_dim[2]);
+		uint32_t maxr = cfg->volume_res[0] > cfg->volume_res[1] ? cfg->volume_res[0] : cfg->volume_res[1];
+		if (cfg->volume_res[2] > maxr) maxr = cfg->volume_res[2];
+		c->step = mind / (float) maxr;
+	}
+	// gaussian (cpp/kernels.cpp:101-107): integer x, integer -(x*x)
+	for (unsigned i = 0; i < (unsigned) (c_radius * 2 + 1); ++i) {
+		const int x = (int) i - 2;
+		c->gaussian[i] = expf(-(x * x) / (2 * c_delta * c_delta));
+	}
+	c->z0 = cfg->slab_z0; c->z1 = cfg->slab_z1;
+	if (c->z0 == 0 && c->z1 == 0) c->z1 = cfg->volume_res[2];
+	if (c->z1 > cfg->volume_res[2] || c->z0 >= c->z1) { delete c; return set_err(KFB_E_ARG, "bad z-slab [%u,%u)", cfg->slab_z0, cfg->slab_z1); }
+	c->slab_voxels = (size_t) cfg->volume_res[0] * cfg->volume_res[1] * (c->z1 - c->z0);
+	c->timing = false;
+	c->rank = 0; c->world = 1; c->nccl_comm = nullptr;
+	c->n_reg = 0;
+	c->d_input = nullptr; c->input_bytes = 0; c->h_stage = nullptr; c->stage_bytes = 0;
+	c->d_render = nullptr; c->render_bytes = 0;
+	c->seq = 0; c->integrate_count = 0;
+
+	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	const size_t P = (size_t) c->cw * c->ch;
+	CK(cudaMalloc(&c->d_vol, c->slab_voxels * sizeof(short2)));
+	CK(cudaMalloc(&c->d_vertex, P * 3 * sizeof(float)));
+	CK(cudaMalloc(&c->d_normal, P * 3 * sizeof(float)));
+	CK(cudaMalloc(&c->d_floatDepth, P * sizeof(float)));
+	// calloc'd in the reference (cpp/kernels.cpp:75-98): first-frame reads of `vertex`/`normal` see zeros
+	CK(cudaMemsetAsync(c->d_vertex, 0, P * 3 * sizeof(float), c->stream));
+	CK(cudaMemsetAsync(c->d_normal, 0, P * 3 * sizeof(float), c->stream));
+	CK(cudaMemsetAsync(c->d_floatDepth, 0, P * sizeof(float), c->stream));
+	for (int l = 0; l < c->levels; ++l) {
+		const size_t n = (size_t) c->lw[l] * c->lh[l];
+		CK(cudaMalloc(&c->d_scaled[l], n * sizeof(float)));
+		CK(cudaMalloc(&c->d_inV[l], n * 3 * sizeof(float)));
+		CK(cudaMalloc(&c->d_inN[l], n * 3 * sizeof(float)));
+		CK(cudaMemsetAsync(c->d_scaled[l], 0, n * sizeof(float), c->stream));
+		CK(cudaMemsetAsync(c->d_inV[l], 0, n * 3 * sizeof(float), c->stream));
+		CK(cudaMemsetAsync(c->d_inN[l], 0, n * 3 * sizeof(float), c->stream));
+	}
+	CK(cudaMalloc(&c->d_status, P));
+	CK(cudaMemsetAsync(c->d_status, 0, P, c->stream));
+	CK(cudaMalloc(&c->d_partials, (size_t) TR_MAX_BLOCKS * 32 * sizeof(double)));
+	CK(cudaMalloc(&c->d_counter, sizeof(unsigned int)));
+	CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
+	CK(cudaMalloc(&c->d_out32, 32 * sizeof(float)));
+	CK(cudaMemsetAsync(c->d_out32, 0, 32 * sizeof(float), c->stream));
+	CK(cudaHostAlloc(&c->h_out32, 64 * sizeof(float), cudaHostAllocMapped));
+	memset(c->h_out32, 0, 64 * sizeof(float));
+	CK(cudaHostGetDevicePointer(&c->h_out32_dev, c->h_out32, 0));
+	CK(cudaMalloc(&c->d_nupd, NUPD_SLOTS * sizeof(unsigned long long)));
+	CK(cudaMemsetAsync(c->d_nupd, 0, NUPD_SLOTS * sizeof(unsigned long long), c->stream));
+	// single-slab view by default
+	memset(&c->view_all, 0, sizeof c->view_all);
+	c->view_all.n_slabs = 1;
+	c->view_all.slab_ptr[0] = c->d_vol;
+	c->view_all.slab_z[0] = c->z0; c->view_all.slab_z[1] = c->z1;
+	c->view_all.sx = cfg->volume_res[0]; c->view_all.sy = cfg->volume_res[1]; c->view_all.sz = cfg->volume_res[2];
+	c->view_all.dx = cfg->volume_dim[0]; c->view_all.dy = cfg->volume_dim[1]; c->view_all.dz = cfg->volume_dim[2];
+	for (int i = 0; i < KFB_MAX_SLABS; ++i) c->peer_ptrs[i] = nullptr;
+	int rc = launch_init_volume(c);
+	if (rc) return rc;
+	CK(cudaStreamSynchronize(c->stream));
+	*out = c;
+	return 0;
+}
+
+int kfb_destroy(kfb_ctx* c) {
+	if (!c) return 0;
+	cudaSetDevice(c->device);
+	cudaStreamSynchronize(c->stream);
+	for (int i = 0; i < c->n_reg; ++i) cudaHostUnregister((void*) c->reg_ptr[i]);
+	for (int i = 0; i < KFB_MAX_SLABS; ++i) if (c->peer_ptrs[i]) cudaIpcCloseMemHandle(c->peer_ptrs[i]);
+	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_floatDepth);
+	for (int l = 0; l < c->levels; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
+	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd);
+	cudaFreeHost(c->h_out32);
+	if (c->d_input) cudaFree(c->d_input);
+	if (c->h_stage) cudaFreeHost(c->h_stage);
+	if (c->d_render) cudaFree(c->d_render);
+	timer_free(c->t_pre); timer_free(c->t_track); timer_free(c->t_int); timer_free(c->t_ray);
+	cudaStreamDestroy(c->stream);
+	delete c;
+	return 0;
+}
+
+int kfb_reset(kfb_ctx* c) {
+	if (!c) return set_err(KFB_E_ARG, "null ctx");
+	CK(cudaSetDevice(c->device));
+	return launch_init_volume(c);
+}
+
+int kfb_sync(kfb_ctx* c) {
+	if (!c) return set_err(KFB_E_ARG, "null ctx");
+	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+int kfb_stream(kfb_ctx* c, void** s) { *s = (void*) c->stream; return 0; }
+int kfb_get_pose(kfb_ctx* c, float pose[16]) { memcpy(pose, c->pose, sizeof c->pose); return 0; }
+int kfb_set_pose(kfb_ctx* c, const float pose[16]) { memcpy(c->pose, pose, sizeof c->pose); return 0; }
+
+// ------------------------------------------------------------------------- preprocessing
+static int check_ratio(kfb_ctx* c, uint32_t iw, uint32_t ih, int* ratio) {
+	// mm2metersKernel's input validation (cpp/kernels.cpp:565-577); the reference prints
+	// "Invalid ratio." and exit(1)s — the C ABI reports it, the Kfusion glue exits.
+	if (iw < c->cw || ih < c->ch || iw % c->cw != 0 || ih % c->ch != 0 || iw / c->cw != ih / c->ch)
+		return set_err(KFB_E_ARG, "Invalid ratio.");
+	*ratio = iw / c->cw;
+	return 0;
+}
+static int launch_preprocess(kfb_ctx* c, const uint16_t* d_in, uint32_t iw, int ratio) {
+	Gauss5 g;
+	memcpy(g.g, c->gaussian, sizeof g.g);
+	dim3 grid((c->cw + PP_BX - 1) / PP_BX, (c->ch + PP_BY - 1) / PP_BY), block(PP_BX, PP_BY);
+	k_mm2m_bilateral<<<grid, block, 0, c->stream>>>(d_in, iw, ratio, c->d_floatDepth, c->d_scaled[0], c->cw, c->ch, g, c_e_delta);
+	LAUNCHED(c);
+	CK(cudaGetLastError());
+	return 0;
+}
+static int ensure_input(kfb_ctx* c, size_t bytes) {
+	if (c->input_bytes >= bytes) return 0;
+	if (c->d_input) CK(cudaFree(c->d_input));
+	CK(cudaMalloc(&c->d_input, bytes));
+	c->input_bytes = bytes;
+	return 0;
+}
+
+int kfb_preprocess(kfb_ctx* c, const uint16_t* depth, uint32_t iw, uint32_t ih) {
+	if (!c || !depth) return set_err(KFB_E_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	int ratio, rc;
+	if ((rc = check_ratio(c, iw, ih, &ratio))) return rc;
+	const size_t bytes = (size_t) iw * ih * sizeof(uint16_t);
+	if ((rc = ensure_input(c, bytes))) return rc;
+	timer_begin(c, c->t_pre);
+	// Is the caller's buffer already page-locked (ours, torch's pinned pool, or registered before)?
+	bool pinned = false;
+	for (int i = 0; i < c->n_reg; ++i) if (c->reg_ptr[i] == depth && c->reg_bytes[i] >= bytes) pinned = true;
+	if (!pinned) {
+		cudaPointerAttributes at;
+		if (cudaPointerGetAttributes(&at, depth) == cudaSuccess && at.type == cudaMemoryTypeHost) pinned = true;
+		else cudaGetLastError();
+	}
+	if (!pinned && c->n_reg < 4) {
+		// benchmark.cpp:103 mallocs ONE frame buffer and reuses it: pin it once, DMA directly afterwards
+		if (cudaHostRegister((void*) depth, bytes, cudaHostRegisterDefault) == cudaSuccess) {
+			c->reg_ptr[c->n_reg] = depth; c->reg_bytes[c->n_reg] = bytes; c->n_reg++;
+			pinned = true;
+		} else cudaGetLastError();
+	}
+	if (pinned) {
+		CK(cudaMemcpyAsync(c->d_input, depth, bytes, cudaMemcpyHostToDevice, c->stream));
+	} else {
+		if (c->stage_bytes < bytes) {
+			if (c->h_stage) CK(cudaFreeHost(c->h_stage));
+			CK(cudaHostAlloc(&c->h_stage, bytes, cudaHostAllocDefault));
+			c->stage_bytes = bytes;
+		}
+		CK(cudaStreamSynchronize(c->stream));  // the staging buffer may still be in flight
+		memcpy(c->h_stage, depth, bytes);
+		CK(cudaMemcpyAsync(c->d_input, c->h_stage, bytes, cudaMemcpyHostToDevice, c->stream));
+	}
+	c->st.h2d_bytes += bytes;
+	rc = launch_preprocess(c, c->d_input, iw, ratio);
+	timer_end(c, c->t_pre);
+	return rc;
+}
+
+int kfb_preprocess_device(kfb_ctx* c, const uint16_t* d_depth, uint32_t iw, uint32_t ih) {
+	if (!c || !d_depth) return set_err(KFB_E_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	int ratio, rc;
+	if ((rc = check_ratio(c, iw, ih, &ratio))) return rc;
+	timer_begin(c, c->t_pre);
+	rc = launch_preprocess(c, d_depth, iw, ratio);
+	timer_end(c, c->t_pre);
+	return rc;
+}
+
+// ------------------------------------------------------------------------------ tracking
+static int launch_pyramid(kfb_ctx* c, const float k[4]) {
+	PyrParams p;
+	memset(&p, 0, sizeof p);
+	p.d0 = c->d_scaled[0];
+	p.levels = c->levels;
+	p.e_d = c_e_delta * 3;
+	uint32_t first = 0;
+	for (int l = 0; l < c->levels; ++l) {
+		p.depth[l] = c->d_scaled[l]; p.vertex[l] = c->d_inV[l]; p.normal[l] = c->d_inN[l];
+		p.w[l] = c->lw[l]; p.h[l] = c->lh[l];
+		p.first[l] = first;
+		first += c->lw[l] * c->lh[l];
+		// getInverseCameraMatrix(k / float(1 << i))   cpp/kernels.cpp:940
+		const float s = (float) (1 << l);
+		const float ks[4] = { k[0] / s, k[1] / s, k[2] / s, k[3] / s };
+		hm_inverse_camera_matrix(p.invK[l].m, ks);
+	}
+	p.first[c->levels] = first;
+	k_pyramid<<<(first + 255) / 256, 256, 0, c->stream>>>(p);
+	LAUNCHED(c);
+	CK(cudaGetLastError());
+	return 0;
+}
+
+static uint32_t track_blocks(uint32_t npx) {
+	uint32_t b = (npx + TR_THREADS - 1) / TR_THREADS;
+	if (b > 148 * 4) b = 148 * 4;
+	if (b < 1) b = 1;
+	return b;
+}
+
+// one fused track+reduce launch; result lands in c->h_out32 (mapped) when wait == true
+static int launch_track(kfb_ctx* c, int level, const float* T, const float* V, float dist, float nthr, bool wait) {
+	TrackParams p;
+	memset(&p, 0, sizeof p);
+	p.inV = c->d_inV[level]; p.inN = c->d_inN[level];
+	p.refV = c->d_vertex; p.refN = c->d_normal;
+	p.w = c->lw[level]; p.h = c->lh[level]; p.rw = c->cw; p.rh = c->ch;
+	p.row0 = 0; p.row1 = p.h;
+	p.Ttrack = toMat(T); p.view = toMat(V);
+	p.pose_dev = nullptr; p.view_dev = nullptr;
+	p.dist_threshold = dist; p.normal_threshold = nthr;
+	p.partials = c->d_partials; p.counter = c->d_counter; p.out32 = c->d_out32;
+	p.out32_host = c->h_out32_dev;
+	p.seq_host = (volatile uint32_t*) (c->h_out32_dev + 32);
+	p.seq = ++c->seq;
+	p.status = (c->cfg.flags & KFB_FLAG_TRACK_STATUS) ? c->d_status : nullptr;
+	const uint32_t blocks = track_blocks(p.w * (p.row1 - p.row0));
+	k_track_reduce<<<blocks, TR_THREADS, 0, c->stream>>>(p);
+	LAUNCHED(c);
+	CK(cudaGetLastError());
+	if (wait) {
+		volatile uint32_t* flag = (volatile uint32_t*) (c->h_out32 + 32);
+		// spin on the mapped flag; fall back to a stream query so a faulted kernel cannot hang us
+		uint64_t spins = 0;
+		while (*flag != p.seq) {
+			if ((++spins & 0xfffff) == 0) {
+				cudaError_t q = cudaStreamQuery(c->stream);
+				if (q != cudaErrorNotReady && q != cudaSuccess) return set_err(KFB_E_CUDA, "track kernel failed: %s", cudaGetErrorString(q));
+				if (q == cudaSuccess && *flag != p.seq) return set_err(KFB_E_CUDA, "track kernel finished without publishing its result");
+			}
+		}
+		__sync_synchronize();
+		memcpy(c->reduction, c->h_out32, 32 * sizeof(float));
+		c->st.d2h_bytes += 32 * sizeof(float);
+	}
+	return 0;
+}
+
+int kfb_k_pyramid(kfb_ctx* c, const float k[4]) {
+	CK(cudaSetDevice(c->device));
+	return launch_pyramid(c, k);
+}
+
+int kfb_k_track_reduce(kfb_ctx* c, int level, const float T[16], const float V[16], float dist, float nthr, float out32[32]) {
+	if (level < 0 || level >= c->levels) return set_err(KFB_E_ARG, "level %d out of range", level);
+	CK(cudaSetDevice(c->device));
+	int rc = launch_track(c, level, T, V, dist, nthr, true);
+	if (rc) return rc;
+	if (out32) memcpy(out32, c->reduction, 32 * sizeof(float));
+	return 0;
+}
+
+int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracking_rate, uint32_t frame, int* tracked) {
+	if (!c || !k) return set_err(KFB_E_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	if (tracked) *tracked = 0;
+	if (tracking_rate == 0) return set_err(KFB_E_ARG, "tracking_rate must be > 0");
+	if (frame % tracking_rate != 0) return 0;                       // cpp/kernels.cpp:927
+	timer_begin(c, c->t_track);
+	int rc = launch_pyramid(c, k);                                  // :931-945
+	if (rc) return rc;
+	memcpy(c->oldPose, c->pose, sizeof c->pose);                    // :947
+	float K[16], invRP[16], projectReference[16];
+	hm_camera_matrix(K, k);
+	hm_inverse4(invRP, c->raycastPose);
+	hm_matmul4(projectReference, K, invRP);                         // :948
+	uint64_t iters = 0;
+	for (int level = c->levels - 1; level >= 0; --level) {         // :950-967
+		for (int i = 0; i < c->cfg.iterations[level]; ++i) {
+			rc = launch_track(c, level, c->pose, projectReference, c_dist_threshold, c_normal_threshold, true);
+			if (rc) return rc;
+			++iters;
+			if (hm_update_pose(c->pose, c->reduction, icp_threshold)) break;
+		}
+	}
+	timer_end(c, c->t_track);
+	c->st.icp_iterations_last = iters;
+	c->st.icp_iterations_total += iters;
+	const int ok = hm_check_pose(c->pose, c->oldPose, c->reduction, c->cw, c->ch, c_track_threshold);  // :968
+	if (tracked) *tracked = ok;
+	return 0;
+}
+
+// --------------------------------------------------------------------------- integration
+static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, float mu, float maxweight) {
+	IntegrateParams p;
+	p.vol = c->d_vol;
+	p.sx = c->cfg.volume_res[0]; p.sy = c->cfg.volume_res[1]; p.sz = c->cfg.volume_res[2];
+	p.dx = c->cfg.volume_dim[0]; p.dy = c->cfg.volume_dim[1]; p.dz = c->cfg.volume_dim[2];
+	p.z_begin = c->z0; p.z_end = c->z1;
+	p.depth = c->d_floatDepth; p.dw = c->cw; p.dh = c->ch;
+	p.invTrack = toMat(invTrack); p.K = toMat(K);
+	p.mu = mu; p.maxweight = maxweight;
+	const uint32_t slot = (uint32_t) (c->integrate_count % NUPD_SLOTS);
+	if (c->integrate_count >= NUPD_SLOTS) CK(cudaMemsetAsync(c->d_nupd + slot, 0, sizeof(unsigned long long), c->stream));
+	p.n_upd = c->d_nupd + slot;
+	// enough z-chunks to put >= ~600k threads in flight (148 SMs x 2048 threads x 2)
+	const uint32_t nz = c->z1 - c->z0;
+	const uint64_t cols = (uint64_t) p.sx * p.sy;
+	uint32_t chunks = (uint32_t) ((148ull * 2048ull * 2ull + cols - 1) / cols);
+	if (chunks < 1) chunks = 1;
+	if (chunks > nz) chunks = nz;
+	p.zchunk = (nz + chunks - 1) / chunks;
+	chunks = (nz + p.zchunk - 1) / p.zchunk;
+	dim3 block(32, 8), grid((p.sx + 31) / 32, (p.sy + 7) / 8, chunks);
+	k_integrate<<<grid, block, 0, c->stream>>>(p);
+	LAUNCHED(c);
+	CK(cudaGetLastError());
+	c->integrate_count++;
+	c->st.frames_integrated++;
+	return 0;
+}
+
+int kfb_k_integrate(kfb_ctx* c, const float invTrack[16], const float K[16], float mu, float maxweight) {
+	CK(cudaSetDevice(c->device));
+	timer_begin(c, c->t_int);
+	int rc = launch_integrate(c, invTrack, K, mu, maxweight);
+	timer_end(c, c->t_int);
+	return rc;
+}
+
+int kfb_integrate(kfb_ctx* c, const float k[4], uint32_t integration_rate, float mu, uint32_t frame, int* integrated) {
+	if (!c || !k) return set_err(KFB_E_ARG, "null argument");
+	if (integration_rate == 0) return set_err(KFB_E_ARG, "integration_rate must be > 0");
+	CK(cudaSetDevice(c->device));
+	int doIntegrate = hm_check_pose(c->pose, c->oldPose, c->reduction, c->cw, c->ch, c_track_threshold);   // cpp/kernels.cpp:991
+	if ((doIntegrate && ((frame % integration_rate) == 0)) || (frame <= 3)) {                               // :994
+		float inv[16], K[16];
+		hm_inverse4(inv, c->pose);
+		hm_camera_matrix(K, k);
+		timer_begin(c, c->t_int);
+		int rc = launch_integrate(c, inv, K, mu, c_maxweight);                                             // :995-996
+		timer_end(c, c->t_int);
+		if (rc) return rc;
+		doIntegrate = 1;
+	} else doIntegrate = 0;
+	if (integrated) *integrated = doIntegrate;
+	return 0;
+}
+
+// ---------------------------------------------------------------------------- raycasting
+static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP, float step, float largestep) {
+	RaycastParams p;
+	p.vol = c->view_all;
+	p.vertex = c->d_vertex; p.normal = c->d_normal;
+	p.w = c->cw; p.h = c->ch;
+	p.row0 = 0; p.row1 = c->ch;
+	p.view = toMat(view);
+	p.nearPlane = nearP; p.farPlane = farP; p.step = step; p.largestep = largestep;
+	dim3 block(RC_BX, RC_BY), grid((p.w + RC_BX - 1) / RC_BX, (p.row1 - p.row0 + RC_BY - 1) / RC_BY);
+	k_raycast<<<grid, block, 0, c->stream>>>(p);
+	LAUNCHED(c);
+	CK(cudaGetLastError());
+	return 0;
+}
+
+int kfb_k_raycast(kfb_ctx* c, const float view[16], float nearP, float farP, float step, float largestep) {
+	CK(cudaSetDevice(c->device));
+	timer_begin(c, c->t_ray);
+	int rc = launch_raycast(c, view, nearP, farP, step, largestep);
+	timer_end(c, c->t_ray);
+	return rc;
+}
+
+int kfb_raycast(kfb_ctx* c, const float k[4], float mu, uint32_t frame) {
+	if (!c || !k) return set_err(KFB_E_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	if (frame > 2) {                                               // cpp/kernels.cpp:977
+		memcpy(c->raycastPose, c->pose, sizeof c->pose);           // :978
+		float invK[16], view[16];
+		hm_inverse_camera_matrix(invK, k);
+		hm_matmul4(view, c->raycastPose, invK);
+		timer_begin(c, c->t_ray);
+		int rc = launch_raycast(c, view, c_nearPlane, c_farPlane, c->step, 0.75f * mu);   // :979-981
+		timer_end(c, c->t_ray);
+		return rc;
+	}
+	return 0;
+}
+
+int kfb_compute_frame(kfb_ctx* c, const uint16_t* depth, uint32_t iw, uint32_t ih, const float k[4], uint32_t integration_rate,
+		uint32_t tracking_rate, float icp_threshold, float mu, uint32_t frame, int* tracked, int* integrated) {
+	int rc;
+	if ((rc = kfb_preprocess(c, depth, iw, ih))) return rc;
+	if ((rc = kfb_track(c, k, icp_threshold, tracking_rate, frame, tracked))) return rc;
+	if ((rc = kfb_integrate(c, k, integration_rate, mu, frame, integrated))) return rc;
+	return kfb_raycast(c, k, mu, frame);
+}
+
+// ------------------------------------------------------------------------------- renders
+static int ensure_render(kfb_ctx* c, size_t bytes) {
+	if (c->render_bytes >= bytes) return 0;
+	if (c->d_render) CK(cudaFree(c->d_render));
+	CK(cudaMalloc(&c->d_render, bytes));
+	c->render_bytes = bytes;
+	return 0;
+}
+static int finish_render(kfb_ctx* c, uint8_t* out, size_t bytes) {
+	CK(cudaGetLastError());
+	CK(cudaMemcpyAsync(out, c->d_render, bytes, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	c->st.d2h_bytes += bytes;
+	return 0;
+}
+int kfb_render_depth(kfb_ctx* c, uint8_t* out, uint32_t w, uint32_t h) {
+	if (w != c->cw || h != c->ch) return set_err(KFB_E_ARG, "render size must equal the computation size");
+	CK(cudaSetDevice(c->device));
+	const uint32_t n = w * h;
+	int rc = ensure_render(c, (size_t) n * 4);
+	if (rc) return rc;
+	k_render_depth<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_render, c->d_floatDepth, n, c_nearPlane, c_farPlane);
+	LAUNCHED(c);
+	return finish_render(c, out, (size_t) n * 4);
+}
+int kfb_render_track(kfb_ctx* c, uint8_t* out, uint32_t w, uint32_t h) {
+	if (w != c->cw || h != c->ch) return set_err(KFB_E_ARG, "render size must equal the computation size");
+	CK(cudaSetDevice(c->device));
+	// the status plane is only maintained on request; the first call switches it on for later frames
+	c->cfg.flags |= KFB_FLAG_TRACK_STATUS;
+	const uint32_t n = w * h;
+	int rc = ensure_render(c, (size_t) n * 4);
+	if (rc) return rc;
+	k_render_track<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_render, c->d_status, n);
+	LAUNCHED(c);
+	return finish_render(c, out, (size_t) n * 4);
+}
+int kfb_render_volume(kfb_ctx* c, uint8_t* out, uint32_t w, uint32_t h, int frame, int rate, const float k[4], float largestep,
+		const float view_pose[16]) {
+	if (rate <= 0) return set_err(KFB_E_ARG, "rendering rate must be > 0");
+	if (frame % rate != 0) return 0;                               // cpp/kernels.cpp:1034
+	CK(cudaSetDevice(c->device));
+	const uint32_t n = w * h;
+	int rc = ensure_render(c, (size_t) n * 4);
+	if (rc) return rc;
+	RenderVolumeParams p;
+	p.vol = c->view_all;
+	p.out = c->d_render; p.w = w; p.h = h;
+	float invK[16], view[16];
+	hm_inverse_camera_matrix(invK, k);
+	hm_matmul4(view, view_pose ? view_pose : c->pose, invK);       // :1036
+	p.view = toMat(view);
+	p.nearPlane = c_nearPlane; p.farPlane = c_farPlane * 2.0f; p.step = c->step; p.largestep = largestep;
+	p.light = make_float3(1, 1, -1.0f); p.ambient = make_float3(0.1f, 0.1f, 0.1f);   // constant_parameters.h:25-26
+	dim3 block(RC_BX, RC_BY), grid((w + RC_BX - 1) / RC_BX, (h + RC_BY - 1) / RC_BY);
+	k_render_volume<<<grid, block, 0, c->stream>>>(p);
+	LAUNCHED(c);
+	return finish_render(c, out, (size_t) n * 4);
+}
+
+int kfb_dump_volume(kfb_ctx* c, const char* path) {
+	if (!path) return 0;                                           // cpp/kernels.cpp:1010
+	CK(cudaSetDevice(c->device));
+	printf("Dumping the volumetric representation on file: %s\n", path);
+	FILE* f = fopen(path, "wb");
+	if (!f) return set_err(KFB_E_ARG, "Error opening file: %s", path);
+	// stream the slab out plane-group by plane-group: tsdf shorts only, x fastest
+	const size_t plane = (size_t) c->cfg.volume_res[0] * c->cfg.volume_res[1];
+	const uint32_t nz = c->z1 - c->z0;
+	const uint32_t zb = (uint32_t) ((((size_t) 64 << 20) / (plane * sizeof(short))) ? (((size_t) 64 << 20) / (plane * sizeof(short))) : 1);
+	short* d_tmp;
+	CK(cudaMalloc(&d_tmp, plane * zb * sizeof(short)));
+	std::vector<short> h(plane * zb);
+	for (uint32_t z = 0; z < nz; z += zb) {
+		const uint32_t nzb = (z + zb <= nz) ? zb : nz - z;
+		const size_t n = plane * nzb;
+		k_extract_tsdf<<<148 * 4, 256, 0, c->stream>>>(d_tmp, c->d_vol + plane * z, n);
+		LAUNCHED(c);
+		CK(cudaMemcpyAsync(h.data(), d_tmp, n * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		fwrite(h.data(), sizeof(short), n, f);
+	}
+	cudaFree(d_tmp);
+	fclose(f);
+	return 0;
+}
+
+// ------------------------------------------------------------------------ buffer access
+static int resolve_buffer(kfb_ctx* c, int which, int level, void** ptr, size_t* bytes, bool* host) {
+	*host = false;
+	const size_t P = (size_t) c->cw * c->ch;
+	if ((which == KFB_BUF_SCALEDDEPTH || which == KFB_BUF_INVERTEX || which == KFB_BUF_INNORMAL) && (level < 0 || level >= c->levels))
+		return set_err(KFB_E_ARG, "level %d out of range", level);
+	const size_t PL = (which == KFB_BUF_SCALEDDEPTH || which == KFB_BUF_INVERTEX || which == KFB_BUF_INNORMAL) ? (size_t) c->lw[level] * c->lh[level] : 0;
+	switch (which) {
+	case KFB_BUF_VOLUME: *ptr = c->d_vol; *bytes = c->slab_voxels * sizeof(short2); break;
+	case KFB_BUF_VERTEX: *ptr = c->d_vertex; *bytes = P * 12; break;
+	case KFB_BUF_NORMAL: *ptr = c->d_normal; *bytes = P * 12; break;
+	case KFB_BUF_FLOATDEPTH: *ptr = c->d_floatDepth; *bytes = P * 4; break;
+	case KFB_BUF_SCALEDDEPTH: *ptr = c->d_scaled[level]; *bytes = PL * 4; break;
+	case KFB_BUF_INVERTEX: *ptr = c->d_inV[level]; *bytes = PL * 12; break;
+	case KFB_BUF_INNORMAL: *ptr = c->d_inN[level]; *bytes = PL * 12; break;
+	case KFB_BUF_REDUCTION: *ptr = c->reduction; *bytes = 32 * 4; *host = true; break;
+	case KFB_BUF_TRACKSTATUS: *ptr = c->d_status; *bytes = P; break;
+	case KFB_BUF_RAYCASTPOSE: *ptr = c->raycastPose; *bytes = 64; *host = true; break;
+	case KFB_BUF_OLDPOSE: *ptr = c->oldPose; *bytes = 64; *host = true; break;
+	case KFB_BUF_GAUSSIAN: *ptr = c->gaussian; *bytes = 20; *host = true; break;
+	case KFB_BUF_INPUTDEPTH: *ptr = c->d_input; *bytes = c->input_bytes; break;
+	default: return set_err(KFB_E_ARG, "unknown buffer %d", which);
+	}
+	return 0;
+}
+int kfb_buffer_bytes(kfb_ctx* c, int which, int level, size_t* bytes) {
+	void* p; bool host;
+	return resolve_buffer(c, which, level, &p, bytes, &host);
+}
+int kfb_device_ptr(kfb_ctx* c, int which, int level, void** dev_ptr) {
+	size_t b; bool host;
+	int rc = resolve_buffer(c, which, level, dev_ptr, &b, &host);
+	if (rc) return rc;
+	if (host) return set_err(KFB_E_ARG, "buffer %d lives on the host", which);
+	return 0;
+}
+int kfb_read_buffer(kfb_ctx* c, int which, int level, void* dst, size_t bytes) {
+	void* p; size_t b; bool host;
+	int rc = resolve_buffer(c, which, level, &p, &b, &host);
+	if (rc) return rc;
+	if (bytes > b) return set_err(KFB_E_ARG, "read of %zu bytes from a %zu-byte buffer", bytes, b);
+	CK(cudaSetDevice(c->device));
+	if (host) { memcpy(dst, p, bytes); return 0; }
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemcpy(dst, p, bytes, cudaMemcpyDeviceToHost));
+	return 0;
+}
+int kfb_write_buffer(kfb_ctx* c, int which, int level, const void* src, size_t bytes) {
+	void* p; size_t b; bool host;
+	int rc = resolve_buffer(c, which, level, &p, &b, &host);
+	if (rc) return rc;
+	if (bytes > b) return set_err(KFB_E_ARG, "write of %zu bytes into a %zu-byte buffer", bytes, b);
+	CK(cudaSetDevice(c->device));
+	if (host) { memcpy(p, src, bytes); return 0; }
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+	return 0;
+}
+
+// -------------------------------------------------------------------------- measurement
+int kfb_enable_timing(kfb_ctx* c, int on) { c->timing = on != 0; return 0; }
+int kfb_reset_stats(kfb_ctx* c) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	timer_resolve(c, c->t_pre); timer_resolve(c, c->t_track); timer_resolve(c, c->t_int); timer_resolve(c, c->t_ray);
+	c->t_pre.total_ms = c->t_track.total_ms = c->t_int.total_ms = c->t_ray.total_ms = 0;
+	c->t_pre.count = c->t_track.count = c->t_int.count = c->t_ray.count = 0;
+	memset(&c->st, 0, sizeof c->st);
+	c->integrate_count = 0;
+	CK(cudaMemset(c->d_nupd, 0, NUPD_SLOTS * sizeof(unsigned long long)));
+	return 0;
+}
+int kfb_get_stats(kfb_ctx* c, kfb_stats* out) {
+	CK(cudaSetDevice(c->device));
+	CK(cudaStreamSynchronize(c->stream));
+	timer_resolve(c, c->t_pre); timer_resolve(c, c->t_track); timer_resolve(c, c->t_int); timer_resolve(c, c->t_ray);
+	std::vector<unsigned long long> h(NUPD_SLOTS);
+	CK(cudaMemcpy(h.data(), c->d_nupd, NUPD_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	unsigned long long tot = 0;
+	for (auto v : h) tot += v;
+	c->st.voxels_updated_total = tot;
+	c->st.voxels_updated_last = c->integrate_count ? h[(c->integrate_count - 1) % NUPD_SLOTS] : 0;
+	// totals over all calls since reset_stats (ms_* hold the SUM; divide by the call counts yourself)
+	c->st.ms_preprocess = (float) c->t_pre.total_ms;
+	c->st.ms_track = (float) c->t_track.total_ms;
+	c->st.ms_integrate = (float) c->t_int.total_ms;
+	c->st.ms_raycast = (float) c->t_ray.total_ms;
+	*out = c->st;
+	return 0;
+}
+
+// ---------------------------------------------------------------------------- multi-GPU
+int kfb_slab_ipc_handle(kfb_ctx* c, uint8_t handle64[64]) {
+	CK(cudaSetDevice(c->device));
+	cudaIpcMemHandle_t h;
+	CK(cudaIpcGetMemHandle(&h, c->d_vol));
+	static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	memcpy(handle64, &h, 64);
+	return 0;
+}
+int kfb_slab_import(kfb_ctx* c, int rank, int world, const uint8_t* handles64, const uint32_t* z_begin) {
+	if (world < 1 || world > KFB_MAX_SLABS || rank < 0 || rank >= world) return set_err(KFB_E_ARG, "bad rank/world %d/%d", rank, world);
+	CK(cudaSetDevice(c->device));
+	c->rank = rank; c->world = world;
+	c->view_all.n_slabs = world;
+	for (int r = 0; r < world; ++r) {
+		c->view_all.slab_z[r] = z_begin[r];
+		if (r == rank) { c->view_all.slab_ptr[r] = c->d_vol; continue; }
+		cudaIpcMemHandle_t h;
+		memcpy(&h, handles64 + 64 * (size_t) r, 64);
+		void* p = nullptr;
+		CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+		c->peer_ptrs[r] = p;
+		c->view_all.slab_ptr[r] = (const short2*) p;
+	}
+	c->view_all.slab_z[world] = c->cfg.volume_res[2];
+	if (z_begin[rank] != c->z0) return set_err(KFB_E_ARG, "z_begin[%d]=%u does not match this context's slab start %u", rank, z_begin[rank], c->z0);
+	return 0;
+}
+int kfb_attach_nccl(kfb_ctx* c, void* comm, int rank, int world) {
+	c->nccl_comm = comm; c->rank = rank; c->world = world;
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,583 @@
+// Hand-written sm_100a kernels of the KinectFusion per-frame pipeline.
+// Each kernel cites the reference function whose results it reproduces
+// (kfusion/src/cpp/kernels.cpp, kfusion/include/commons.h).  None of these stages is a dense
+// contraction, so there is no tensor-core work: they are HBM/L2-bound streaming, stencil,
+// gather and reduction kernels.  Compiled with --fmad=false -prec-div=true -prec-sqrt=true:
+// parity with the reference's un-fused IEEE fp32 arithmetic is bit-exact by construction for
+// every stage except the (order-dependent) ICP sums.
+#ifndef KFB_KERNELS_CUH
+#define KFB_KERNELS_CUH
+
+#include "kfb_math.cuh"
+#include "kfb_expf.h"
+#include "kfb_hostmath.h"
+
+// ------------------------------------------------------------------------------------------
+// initVolumeKernel (cpp/kernels.cpp:147-157): every voxel <- short2(32766, 0).  128-bit stores.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_init_volume(uint4* __restrict__ vol4, size_t n4, short2* __restrict__ vol, size_t n) {
+	const uint32_t v = (uint32_t) (uint16_t) 32766;  // x = 32766, y = 0
+	const size_t stride = (size_t) gridDim.x * blockDim.x;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) vol4[i] = make_uint4(v, v, v, v);
+	// tail (n not a multiple of 4 voxels)
+	for (size_t i = n4 * 4 + (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) vol[i] = make_short2(32766, 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// mm2metersKernel + bilateralFilterKernel fused (cpp/kernels.cpp:562-589, 159-198).
+// One 32x8 output tile per CTA; the (32+4)x(8+4) halo tile of metres is staged in shared
+// memory straight from the uint16 sensor frame, so the raw float depth is never re-read.
+// Writes BOTH the raw depth (integrate consumes it, :995) and the filtered depth (:918).
+// Border taps clamp to the edge exactly like the host `clamp(uint,..)` does.
+// ------------------------------------------------------------------------------------------
+struct Gauss5 { float g[5]; };
+
+#define PP_BX 32
+#define PP_BY 8
+#define PP_R 2
+__global__ void __launch_bounds__(PP_BX* PP_BY) k_mm2m_bilateral(const uint16_t* __restrict__ in, uint32_t iw, int ratio,
+		float* __restrict__ raw, float* __restrict__ filt, uint32_t w, uint32_t h, Gauss5 gs, float e_d) {
+	__shared__ float tile[PP_BY + 2 * PP_R][PP_BX + 2 * PP_R + 1];
+	const int x0 = blockIdx.x * PP_BX, y0 = blockIdx.y * PP_BY;
+	const int tid = threadIdx.y * PP_BX + threadIdx.x;
+	for (int i = tid; i < (PP_BY + 2 * PP_R) * (PP_BX + 2 * PP_R); i += PP_BX * PP_BY) {
+		const int ty = i / (PP_BX + 2 * PP_R), tx = i - ty * (PP_BX + 2 * PP_R);
+		const int gx = kmaxi(0, kmini(x0 + tx - PP_R, (int) w - 1));
+		const int gy = kmaxi(0, kmini(y0 + ty - PP_R, (int) h - 1));
+		tile[ty][tx] = (float) in[(size_t) gx * ratio + (size_t) iw * gy * ratio] / 1000.0f;
+	}
+	__syncthreads();
+	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+	if (x >= (int) w || y >= (int) h) return;
+	const float center = tile[threadIdx.y + PP_R][threadIdx.x + PP_R];
+	const size_t pos = (size_t) x + (size_t) y * w;
+	raw[pos] = center;
+	if (center == 0) { filt[pos] = 0; return; }
+	const float e_d_squared_2 = e_d * e_d * 2;
+	float sum = 0.0f, t = 0.0f;
+#pragma unroll
+	for (int i = -PP_R; i <= PP_R; ++i) {      // i walks x, j walks y — the reference's order
+#pragma unroll
+		for (int j = -PP_R; j <= PP_R; ++j) {
+			const float curPix = tile[threadIdx.y + PP_R + j][threadIdx.x + PP_R + i];
+			if (curPix > 0) {
+				const float mod = ksq(curPix - center);
+				const float factor = gs.g[i + PP_R] * gs.g[j + PP_R] * kfb_expf_nonpos(-mod / e_d_squared_2);
+				t += factor * curPix;
+				sum += factor;
+			}
+		}
+	}
+	filt[pos] = t / sum;
+}
+
+// ------------------------------------------------------------------------------------------
+// Pyramid + vertex/normal maps in ONE launch (cpp/kernels.cpp:931-945):
+//   halfSampleRobustImageKernel (:591-626) for levels 1..L-1,
+//   depth2vertexKernel (:200-218) and vertex2normalKernel (:220-249) for levels 0..L-1.
+// One thread per output pixel of every level.  Coarse depths are RECOMPUTED from level 0
+// (4 or 16 L1-resident loads) instead of being produced by a chain of dependent launches;
+// the recomputation performs the identical fp32 operations, so the result is bit-identical.
+// ------------------------------------------------------------------------------------------
+struct PyrParams {
+	const float* d0;          // ScaledDepth[0]
+	float* depth[3];          // ScaledDepth[l] (l>=1 written here)
+	float* vertex[3];
+	float* normal[3];
+	uint32_t w[3], h[3];
+	uint32_t first[4];        // first linear thread id of each level (prefix sums), first[L] = total
+	Mat4 invK[3];
+	int levels;
+	float e_d;                // e_delta * 3
+};
+
+// robust 2x2 mean of `in` (size iw x ..) at output pixel (x,y): r = 1 => offsets {0,1}
+template <class F> __device__ __forceinline__ float half_sample(F in, int x, int y, float e_d) {
+	const int cx = 2 * x, cy = 2 * y;
+	float sum = 0.0f, t = 0.0f;
+	const float center = in(cx, cy);
+#pragma unroll
+	for (int i = 0; i <= 1; ++i)
+#pragma unroll
+		for (int j = 0; j <= 1; ++j) {
+			const float current = in(cx + j, cy + i);
+			if (fabsf(current - center) < e_d) { sum += 1.0f; t += current; }
+		}
+	return t / sum;
+}
+
+__device__ __forceinline__ float pyr_depth(const PyrParams& p, int level, int x, int y) {
+	const float* d0 = p.d0;
+	const uint32_t w0 = p.w[0];
+	auto l0 = [&](int xx, int yy) { return __ldg(d0 + (size_t) xx + (size_t) yy * w0); };
+	if (level == 0) return l0(x, y);
+	auto l1 = [&](int xx, int yy) { return half_sample(l0, xx, yy, p.e_d); };
+	if (level == 1) return l1(x, y);
+	return half_sample(l1, x, y, p.e_d);
+}
+
+__device__ __forceinline__ float3 pyr_vertex(const PyrParams& p, int level, int x, int y) {
+	const float d = pyr_depth(p, level, x, y);
+	if (d > 0) return d * mat_rotate(p.invK[level], f3((float) x, (float) y, 1.f));
+	return f3(0, 0, 0);
+}
+
+__global__ void __launch_bounds__(256) k_pyramid(PyrParams p) {
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= p.first[p.levels]) return;
+	int level = 0;
+	if (p.levels > 1 && tid >= p.first[1]) level = 1;
+	if (p.levels > 2 && tid >= p.first[2]) level = 2;
+	const uint32_t local = tid - p.first[level];
+	const int w = p.w[level], h = p.h[level];
+	const int x = local % w, y = local / w;
+	if (level > 0) p.depth[level][local] = pyr_depth(p, level, x, y);
+	const float3 v = pyr_vertex(p, level, x, y);
+	st3(p.vertex[level], local, v);
+	const float3 left = pyr_vertex(p, level, kmaxi(x - 1, 0), y);
+	const float3 right = pyr_vertex(p, level, kmini(x + 1, w - 1), y);
+	const float3 up = pyr_vertex(p, level, x, kmaxi(y - 1, 0));
+	const float3 down = pyr_vertex(p, level, x, kmini(y + 1, h - 1));
+	if (left.z == 0 || right.z == 0 || up.z == 0 || down.z == 0) {
+		p.normal[level][3 * (size_t) local] = KFB_INVALID;  // only .x, like the reference (:240)
+		return;
+	}
+	const float3 dxv = right - left, dyv = down - up;
+	st3(p.normal[level], local, knormalize(kcross(dyv, dxv)));
+}
+
+// ------------------------------------------------------------------------------------------
+// trackKernel + reduceKernel FUSED (cpp/kernels.cpp:497-560, 251-495).
+// The reference writes a 32-byte TrackData per pixel to memory and re-reads it in a second
+// kernel; here each thread folds its pixels straight into 27 register sums + 4 counters,
+// warps combine with shuffles, CTAs through shared memory, and the last CTA to finish sums
+// the per-CTA partials in a FIXED order (deterministic, no float atomics) into the 32-float
+// result: [0]=sum e^2, [1..6]=J^T e, [7..27]=upper-tri J^T J, [28]=#inliers, [29]=#(-4),
+// [30]=#(-5), [31]=#(-1,-2,-3).  Cross-thread accumulation is fp64, so the result does not
+// depend on the grid shape beyond ~1e-16 and multi-GPU partial sums compose.
+// ------------------------------------------------------------------------------------------
+#define TR_THREADS 256
+#define TR_MAX_BLOCKS 1184  // 148 SMs x 8
+
+struct TrackParams {
+	const float* inV; const float* inN;     // packed float3[w*h] of this level
+	const float* refV; const float* refN;   // packed float3[rw*rh] (raycast maps, world frame)
+	uint32_t w, h, rw, rh;
+	uint32_t row0, row1;                    // this context's share of input rows [row0,row1) (multi-GPU: a band)
+	Mat4 Ttrack, view;                      // pose, projectReference (used when pose_dev == nullptr)
+	const float* pose_dev;                  // optional: pose / view live in device memory (device-side ICP loop)
+	const float* view_dev;
+	float dist_threshold, normal_threshold;
+	double* partials;                       // [gridDim.x][32]
+	unsigned int* counter;                  // last-block ticket
+	float* out32;                           // device result
+	float* out32_host; volatile uint32_t* seq_host; uint32_t seq;  // optional mapped-host mirror + sequence flag
+	int8_t* status;                         // optional per-pixel result plane (stride rw), for renderTrack
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+	return v;
+}
+
+
+__global__ void __launch_bounds__(TR_THREADS) k_track_reduce(TrackParams p) {
+	__shared__ double sm[TR_THREADS / 32][32];
+	__shared__ bool is_last;
+	Mat4 T, V;
+	if (p.pose_dev) {
+#pragma unroll
+		for (int i = 0; i < 16; ++i) { T.m[i] = p.pose_dev[i]; V.m[i] = p.view_dev[i]; }
+	} else { T = p.Ttrack; V = p.view; }
+
+	float s[28];
+#pragma unroll
+	for (int i = 0; i < 28; ++i) s[i] = 0.f;
+	int c28 = 0, c29 = 0, c30 = 0, c31 = 0;
+
+	const uint32_t npx = (p.row1 - p.row0) * p.w;
+	for (uint32_t i = blockIdx.x * TR_THREADS + threadIdx.x; i < npx; i += gridDim.x * TR_THREADS) {
+		const uint32_t py = p.row0 + i / p.w, px = i % p.w;
+		const size_t idx = (size_t) px + (size_t) py * p.w;
+		int result;
+		float err = 0.f;
+		float3 Ja = f3(0, 0, 0), Jb = f3(0, 0, 0);
+		const float3 n = ld3(p.inN, idx);
+		if (n.x == KFB_INVALID) {
+			result = -1;
+		} else {
+			const float3 pv = mat_point(T, ld3(p.inV, idx));
+			const float3 pp = mat_point(V, pv);
+			const float pixx = pp.x / pp.z + 0.5f, pixy = pp.y / pp.z + 0.5f;
+			if (pixx < 0 || pixx > (float) (p.rw - 1) || pixy < 0 || pixy > (float) (p.rh - 1)) {
+				result = -2;
+			} else {
+				// (uint)NaN is 0 on x86-64 (cvttss2si, low 32 bits) and here (cvt.rzi) — start-up frames
+				const uint32_t rx = (uint32_t) pixx, ry = (uint32_t) pixy;
+				const size_t ridx = (size_t) rx + (size_t) ry * p.rw;
+				const float3 rn = ld3(p.refN, ridx);
+				if (rn.x == KFB_INVALID) {
+					result = -3;
+				} else {
+					const float3 diff = ld3(p.refV, ridx) - pv;
+					const float3 pn = mat_rotate(T, n);
+					if (klength(diff) > p.dist_threshold) result = -4;
+					else if (kdot(pn, rn) < p.normal_threshold) result = -5;
+					else {
+						result = 1;
+						err = kdot(rn, diff);
+						Ja = rn;
+						Jb = kcross(pv, rn);
+					}
+				}
+			}
+		}
+		if (p.status) p.status[(size_t) px + (size_t) py * p.rw] = (int8_t) result;
+		if (result < 1) {
+			c29 += (result == -4);
+			c30 += (result == -5);
+			c31 += (result > -4);
+		} else {
+			const float J[6] = { Ja.x, Ja.y, Ja.z, Jb.x, Jb.y, Jb.z };
+			s[0] += err * err;
+#pragma unroll
+			for (int k = 0; k < 6; ++k) s[1 + k] += err * J[k];
+			int q = 7;
+#pragma unroll
+			for (int a = 0; a < 6; ++a)
+#pragma unroll
+				for (int b = a; b < 6; ++b) s[q++] += J[a] * J[b];
+			c28 += 1;
+		}
+	}
+
+	// warp -> CTA -> grid, all in fp64 and in a fixed order
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+	for (int i = 0; i < 28; ++i) {
+		const double v = warp_sum((double) s[i]);
+		if (lane == 0) sm[wid][i] = v;
+	}
+	{
+		const double v28 = warp_sum((double) c28), v29 = warp_sum((double) c29), v30 = warp_sum((double) c30), v31 = warp_sum((double) c31);
+		if (lane == 0) { sm[wid][28] = v28; sm[wid][29] = v29; sm[wid][30] = v30; sm[wid][31] = v31; }
+	}
+	__syncthreads();
+	if (wid == 0) {
+		double v = 0;
+#pragma unroll
+		for (int w = 0; w < TR_THREADS / 32; ++w) v += sm[w][lane];
+		p.partials[(size_t) blockIdx.x * 32 + lane] = v;
+		__threadfence();
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		const unsigned int ticket = atomicAdd(p.counter, 1u);
+		is_last = (ticket == gridDim.x - 1);
+	}
+	__syncthreads();
+	if (!is_last) return;
+	__threadfence();
+	// last CTA: warp w sums partial rows w, w+8, ... ; then the 8 warp sums are added in order
+	{
+		double v = 0;
+		for (uint32_t b = wid; b < gridDim.x; b += TR_THREADS / 32) v += __ldcg(p.partials + (size_t) b * 32 + lane);
+		sm[wid][lane] = v;
+	}
+	__syncthreads();
+	if (wid == 0) {
+		double v = 0;
+#pragma unroll
+		for (int w = 0; w < TR_THREADS / 32; ++w) v += sm[w][lane];
+		const float r = (float) v;
+		p.out32[lane] = r;
+		if (p.out32_host) p.out32_host[lane] = r;
+		if (lane == 0) *p.counter = 0;  // re-arm for the next launch
+		__syncwarp();
+		if (p.seq_host) {
+			__threadfence_system();
+			if (lane == 0) *p.seq_host = p.seq;
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// integrateKernel (cpp/kernels.cpp:628-673): TSDF running average over the voxels that
+// project into the depth image.  The reference walks each (x,y) column from z = 0 and
+// advances `pos` / `cameraX` by REPEATED fp32 addition; reproducing those exact values is
+// what keeps every voxel bit-identical (recomputing pos0 + z*delta is off by several LSB,
+// SURVEY §7).  A thread owns one column and a z-chunk; it first replays the additions up
+// to its first z (6 independent FADD chains, no memory traffic), then streams its chunk.
+// x is the fastest thread index, so each warp touches 128 contiguous bytes per z-slice.
+// The kernel is launched on the slab [z_begin, z_end) this context owns; `vol` points at
+// the slab's first voxel.  N_upd (voxels actually updated) is counted exactly.
+// ------------------------------------------------------------------------------------------
+struct IntegrateParams {
+	short2* vol;
+	uint32_t sx, sy, sz;       // full volume resolution
+	float dx, dy, dz;          // volume dimensions (metres)
+	uint32_t z_begin, z_end;   // slab owned by this context
+	uint32_t zchunk;           // z-steps per thread
+	const float* depth; uint32_t dw, dh;
+	Mat4 invTrack, K;
+	float mu, maxweight;
+	unsigned long long* n_upd;
+};
+
+__global__ void __launch_bounds__(256) k_integrate(IntegrateParams p) {
+	const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+	const uint32_t zs = p.z_begin + blockIdx.z * p.zchunk;
+	const uint32_t ze = min(zs + p.zchunk, p.z_end);
+	unsigned int updated = 0;
+	if (x < p.sx && y < p.sy && zs < ze) {
+		const float3 delta = mat_rotate(p.invTrack, f3(0, 0, p.dz / (float) p.sz));
+		const float3 cameraDelta = mat_rotate(p.K, delta);
+		// Volume::pos (commons.h:186-189) at z = 0
+		float3 pos = mat_point(p.invTrack, f3(((float) x + 0.5f) * p.dx / (float) p.sx, ((float) y + 0.5f) * p.dy / (float) p.sy,
+				(0 + 0.5f) * p.dz / (float) p.sz));
+		float3 cameraX = mat_point(p.K, pos);
+		for (uint32_t z = 0; z < zs; ++z) { pos = pos + delta; cameraX = cameraX + cameraDelta; }
+		const size_t plane = (size_t) p.sx * p.sy;
+		short2* col = p.vol + (size_t) x + (size_t) y * p.sx + (size_t) (zs - p.z_begin) * plane;
+		const float dwm1 = (float) (p.dw - 1), dhm1 = (float) (p.dh - 1);
+		for (uint32_t z = zs; z < ze; ++z, pos = pos + delta, cameraX = cameraX + cameraDelta, col += plane) {
+			if (pos.z < 0.0001f) continue;
+			const float pxf = cameraX.x / cameraX.z + 0.5f, pyf = cameraX.y / cameraX.z + 0.5f;
+			if (pxf < 0 || pxf > dwm1 || pyf < 0 || pyf > dhm1) continue;
+			const uint32_t px = (uint32_t) pxf, py = (uint32_t) pyf;
+			const float d = __ldg(p.depth + px + (size_t) py * p.dw);
+			if (d == 0) continue;
+			const float diff = (d - cameraX.z) * sqrtf(1 + ksq(pos.x / pos.z) + ksq(pos.y / pos.z));
+			if (diff > -p.mu) {
+				const float sdf = kminf(1.f, diff / p.mu);
+				const short2 v = *col;
+				float tsdf = (float) v.x * 0.00003051944088f, wgt = (float) v.y;   // commons.h:160-163
+				tsdf = kclampf((wgt * tsdf + sdf) / (wgt + 1), -1.f, 1.f);
+				wgt = kminf(wgt + 1, p.maxweight);
+				*col = make_short2((short) (int) (tsdf * 32766.0f), (short) (int) wgt); // commons.h:182-185 (truncation)
+				++updated;
+			}
+		}
+	}
+	// exact N_upd: one atomic per warp
+	for (int o = 16; o > 0; o >>= 1) updated += __shfl_xor_sync(0xffffffffu, updated, o);
+	if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && updated) atomicAdd(p.n_upd, (unsigned long long) updated);
+}
+
+// ------------------------------------------------------------------------------------------
+// raycastKernel (cpp/kernels.cpp:674-757) with Volume::interp / Volume::grad
+// (commons.h:191-301).  One thread per pixel; `t` advances by repeated fp32 addition and the
+// coarse->fine step switch is history dependent, so rays are marched exactly as the reference
+// does.  The volume may be split into z-slabs owned by different GPUs: slab s holds
+// z in [slab_z[s], slab_z[s+1]) at slab_ptr[s] (peer memory over NVLink when s is remote).
+// ------------------------------------------------------------------------------------------
+#define KFB_MAX_SLABS 8
+struct VolView {
+	const short2* slab_ptr[KFB_MAX_SLABS];
+	uint32_t slab_z[KFB_MAX_SLABS + 1];
+	int n_slabs;
+	uint32_t sx, sy, sz;
+	float dx, dy, dz;
+};
+
+__device__ __forceinline__ float vol_vs2(const VolView& v, int x, int y, int z) {  // commons.h:172-174
+	int s = 0;
+	if (v.n_slabs > 1) {
+#pragma unroll
+		for (int i = 1; i < KFB_MAX_SLABS; ++i) s += (i < v.n_slabs && (uint32_t) z >= v.slab_z[i]);
+	}
+	const short2* base = v.slab_ptr[s];
+	const size_t idx = (size_t) x + (size_t) y * v.sx + (size_t) ((uint32_t) z - v.slab_z[s]) * v.sx * v.sy;
+	return (float) __ldg(reinterpret_cast<const short*>(base + idx));
+}
+
+__device__ __forceinline__ float vol_interp(const VolView& v, float3 pos) {  // commons.h:191-213
+	const float3 sp = f3((pos.x * (float) v.sx / v.dx) - 0.5f, (pos.y * (float) v.sy / v.dy) - 0.5f, (pos.z * (float) v.sz / v.dz) - 0.5f);
+	const float flx = floorf(sp.x), fly = floorf(sp.y), flz = floorf(sp.z);
+	const int bx = (int) flx, by = (int) fly, bz = (int) flz;
+	const float3 f = f3(sp.x - flx, sp.y - fly, sp.z - flz);
+	const int lx = kmaxi(bx, 0), ly = kmaxi(by, 0), lz = kmaxi(bz, 0);
+	const int ux = kmini(bx + 1, (int) v.sx - 1), uy = kmini(by + 1, (int) v.sy - 1), uz = kmini(bz + 1, (int) v.sz - 1);
+	return (((vol_vs2(v, lx, ly, lz) * (1 - f.x) + vol_vs2(v, ux, ly, lz) * f.x) * (1 - f.y)
+			+ (vol_vs2(v, lx, uy, lz) * (1 - f.x) + vol_vs2(v, ux, uy, lz) * f.x) * f.y) * (1 - f.z)
+			+ ((vol_vs2(v, lx, ly, uz) * (1 - f.x) + vol_vs2(v, ux, ly, uz) * f.x) * (1 - f.y)
+					+ (vol_vs2(v, lx, uy, uz) * (1 - f.x) + vol_vs2(v, ux, uy, uz) * f.x) * f.y) * f.z) * 0.00003051944088f;
+}
+
+__device__ __forceinline__ float3 vol_grad(const VolView& v, float3 pos) {  // commons.h:215-301
+	const float3 sp = f3((pos.x * (float) v.sx / v.dx) - 0.5f, (pos.y * (float) v.sy / v.dy) - 0.5f, (pos.z * (float) v.sz / v.dz) - 0.5f);
+	const float flx = floorf(sp.x), fly = floorf(sp.y), flz = floorf(sp.z);
+	const int bx = (int) flx, by = (int) fly, bz = (int) flz;
+	const float3 f = f3(sp.x - flx, sp.y - fly, sp.z - flz);
+	const int mx = (int) v.sx - 1, my = (int) v.sy - 1, mz = (int) v.sz - 1;
+	const int llx = kmaxi(bx - 1, 0), lly = kmaxi(by - 1, 0), llz = kmaxi(bz - 1, 0);     // lower_lower
+	const int lx = kmaxi(bx, 0), ly = kmaxi(by, 0), lz = kmaxi(bz, 0);                    // lower_upper == lower
+	const int ux = kmini(bx + 1, mx), uy = kmini(by + 1, my), uz = kmini(bz + 1, mz);     // upper_lower == upper
+	const int uux = kmini(bx + 2, mx), uuy = kmini(by + 2, my), uuz = kmini(bz + 2, mz);  // upper_upper
+	float3 g;
+#define VS(a, b, c) vol_vs2(v, a, b, c)
+	g.x = (((VS(ux, ly, lz) - VS(llx, ly, lz)) * (1 - f.x) + (VS(uux, ly, lz) - VS(lx, ly, lz)) * f.x) * (1 - f.y)
+			+ ((VS(ux, uy, lz) - VS(llx, uy, lz)) * (1 - f.x) + (VS(uux, uy, lz) - VS(lx, uy, lz)) * f.x) * f.y) * (1 - f.z)
+			+ (((VS(ux, ly, uz) - VS(llx, ly, uz)) * (1 - f.x) + (VS(uux, ly, uz) - VS(lx, ly, uz)) * f.x) * (1 - f.y)
+					+ ((VS(ux, uy, uz) - VS(llx, uy, uz)) * (1 - f.x) + (VS(uux, uy, uz) - VS(lx, uy, uz)) * f.x) * f.y) * f.z;
+	g.y = (((VS(lx, uy, lz) - VS(lx, lly, lz)) * (1 - f.x) + (VS(ux, uy, lz) - VS(ux, lly, lz)) * f.x) * (1 - f.y)
+			+ ((VS(lx, uuy, lz) - VS(lx, ly, lz)) * (1 - f.x) + (VS(ux, uuy, lz) - VS(ux, ly, lz)) * f.x) * f.y) * (1 - f.z)
+			+ (((VS(lx, uy, uz) - VS(lx, lly, uz)) * (1 - f.x) + (VS(ux, uy, uz) - VS(ux, lly, uz)) * f.x) * (1 - f.y)
+					+ ((VS(lx, uuy, uz) - VS(lx, ly, uz)) * (1 - f.x) + (VS(ux, uuy, uz) - VS(ux, ly, uz)) * f.x) * f.y) * f.z;
+	g.z = (((VS(lx, ly, uz) - VS(lx, ly, llz)) * (1 - f.x) + (VS(ux, ly, uz) - VS(ux, ly, llz)) * f.x) * (1 - f.y)
+			+ ((VS(lx, uy, uz) - VS(lx, uy, llz)) * (1 - f.x) + (VS(ux, uy, uz) - VS(ux, uy, llz)) * f.x) * f.y) * (1 - f.z)
+			+ (((VS(lx, ly, uuz) - VS(lx, ly, lz)) * (1 - f.x) + (VS(ux, ly, uuz) - VS(ux, ly, lz)) * f.x) * (1 - f.y)
+					+ ((VS(lx, uy, uuz) - VS(lx, uy, lz)) * (1 - f.x) + (VS(ux, uy, uuz) - VS(ux, uy, lz)) * f.x) * f.y) * f.z;
+#undef VS
+	return g * f3(v.dx / (float) v.sx, v.dy / (float) v.sy, v.dz / (float) v.sz) * (0.5f * 0.00003051944088f);
+}
+
+// cpp/kernels.cpp:674-725; returns hit.xyz, *tw = hit.w
+__device__ __forceinline__ float3 raycast_one(const VolView& v, uint32_t px, uint32_t py, const Mat4& view, float nearPlane,
+		float farPlane, float step, float largestep, float* tw) {
+	const float3 origin = f3(view.m[3], view.m[7], view.m[11]);
+	const float3 direction = mat_rotate(view, f3((float) px, (float) py, 1.f));
+	const float3 invR = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
+	const float3 tbot = (-1.f * invR) * origin;
+	const float3 ttop = invR * (f3(v.dx, v.dy, v.dz) - origin);
+	const float3 tmin = f3(kminf(ttop.x, tbot.x), kminf(ttop.y, tbot.y), kminf(ttop.z, tbot.z));
+	const float3 tmax = f3(kmaxf(ttop.x, tbot.x), kmaxf(ttop.y, tbot.y), kmaxf(ttop.z, tbot.z));
+	const float largest_tmin = kmaxf(kmaxf(tmin.x, tmin.y), kmaxf(tmin.x, tmin.z));   // x twice, as in the reference (:693)
+	const float smallest_tmax = kminf(kminf(tmax.x, tmax.y), kminf(tmax.x, tmax.z));
+	const float tnear = kmaxf(largest_tmin, nearPlane);
+	const float tfar = kminf(smallest_tmax, farPlane);
+	if (tnear < tfar) {
+		float t = tnear;
+		float stepsize = largestep;
+		float f_t = vol_interp(v, origin + direction * t);
+		float f_tt = 0;
+		if (f_t > 0) {
+			for (; t < tfar; t += stepsize) {
+				f_tt = vol_interp(v, origin + direction * t);
+				if (f_tt < 0) break;
+				if (f_tt < 0.8f) stepsize = step;
+				f_t = f_tt;
+			}
+			if (f_tt < 0) {
+				t = t + stepsize * f_tt / (f_t - f_tt);
+				*tw = t;
+				return origin + direction * t;
+			}
+		}
+	}
+	*tw = 0;
+	return f3(0, 0, 0);
+}
+
+struct RaycastParams {
+	VolView vol;
+	float* vertex; float* normal;   // packed float3[w*h]
+	uint32_t w, h;
+	uint32_t row0, row1;            // rows handled by this context (multi-GPU: a band of pixels)
+	Mat4 view;
+	float nearPlane, farPlane, step, largestep;
+};
+
+#define RC_BX 16
+#define RC_BY 16
+__global__ void __launch_bounds__(RC_BX* RC_BY) k_raycast(RaycastParams p) {
+	const uint32_t x = blockIdx.x * RC_BX + threadIdx.x;
+	const uint32_t y = p.row0 + blockIdx.y * RC_BY + threadIdx.y;
+	if (x >= p.w || y >= p.row1) return;
+	const size_t idx = (size_t) x + (size_t) y * p.w;
+	float hw;
+	const float3 hit = raycast_one(p.vol, x, y, p.view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw);
+	if (hw > 0.0f) {
+		st3(p.vertex, idx, hit);
+		const float3 surfNorm = vol_grad(p.vol, hit);
+		if (klength(surfNorm) == 0) p.normal[3 * idx] = KFB_INVALID;  // only .x (:745)
+		else st3(p.normal, idx, knormalize(surfNorm));
+	} else {
+		st3(p.vertex, idx, f3(0, 0, 0));
+		st3(p.normal, idx, f3(KFB_INVALID, 0, 0));
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// render kernels (cpp/kernels.cpp:814-913) — visualisation only, outside "computation"
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uchar4 gs2rgb_dev(double h) {  // commons.h:86-147
+	double r = 0, g = 0, b = 0;
+	const double v = 0.75, m = 0.25, sv = 0.6667;
+	h *= 6.0;
+	const int sextant = (int) h;
+	const double fract = h - sextant, vsf = v * sv * fract, mid1 = m + vsf, mid2 = v - vsf;
+	switch (sextant) {
+	case 0: r = v; g = mid1; b = m; break;
+	case 1: r = mid2; g = v; b = m; break;
+	case 2: r = m; g = v; b = mid1; break;
+	case 3: r = m; g = mid2; b = v; break;
+	case 4: r = mid1; g = m; b = v; break;
+	case 5: r = v; g = m; b = mid2; break;
+	default: r = 0; g = 0; b = 0; break;
+	}
+	return make_uchar4((unsigned char) (int) (r * 255), (unsigned char) (int) (g * 255), (unsigned char) (int) (b * 255), 0);
+}
+
+__global__ void __launch_bounds__(256) k_render_depth(uchar4* out, const float* depth, uint32_t n, float nearPlane, float farPlane) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const float rangeScale = 1 / (farPlane - nearPlane);
+	const float d = depth[i];
+	if (d < nearPlane) out[i] = make_uchar4(255, 255, 255, 0);
+	else if (d > farPlane) out[i] = make_uchar4(0, 0, 0, 0);
+	else out[i] = gs2rgb_dev((d - nearPlane) * rangeScale);
+}
+
+__global__ void __launch_bounds__(256) k_render_track(uchar4* out, const int8_t* status, uint32_t n) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	uchar4 c;
+	switch (status[i]) {
+	case 1: c = make_uchar4(128, 128, 128, 0); break;
+	case -1: c = make_uchar4(0, 0, 0, 0); break;
+	case -2: c = make_uchar4(255, 0, 0, 0); break;
+	case -3: c = make_uchar4(0, 255, 0, 0); break;
+	case -4: c = make_uchar4(0, 0, 255, 0); break;
+	case -5: c = make_uchar4(255, 255, 0, 0); break;
+	default: c = make_uchar4(255, 128, 128, 0); break;
+	}
+	out[i] = c;
+}
+
+struct RenderVolumeParams {
+	VolView vol;
+	uchar4* out;
+	uint32_t w, h;
+	Mat4 view;
+	float nearPlane, farPlane, step, largestep;
+	float3 light, ambient;
+};
+__global__ void __launch_bounds__(RC_BX* RC_BY) k_render_volume(RenderVolumeParams p) {
+	const uint32_t x = blockIdx.x * RC_BX + threadIdx.x, y = blockIdx.y * RC_BY + threadIdx.y;
+	if (x >= p.w || y >= p.h) return;
+	float hw;
+	const float3 test = raycast_one(p.vol, x, y, p.view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw);
+	uchar4 o = make_uchar4(0, 0, 0, 0);
+	if (hw > 0) {
+		const float3 surfNorm = vol_grad(p.vol, test);
+		if (klength(surfNorm) > 0) {
+			const float3 diff = knormalize(p.light - test);
+			const float dir = kmaxf(kdot(knormalize(surfNorm), diff), 0.f);
+			const float3 col = f3(kclampf(dir + p.ambient.x, 0.f, 1.f), kclampf(dir + p.ambient.y, 0.f, 1.f),
+					kclampf(dir + p.ambient.z, 0.f, 1.f)) * 255.f;
+			o = make_uchar4((unsigned char) (int) col.x, (unsigned char) (int) col.y, (unsigned char) (int) col.z, 0);
+		}
+	}
+	p.out[(size_t) x + (size_t) y * p.w] = o;
+}
+
+// dumpVolume helper (cpp/kernels.cpp:1022-1026): gather the tsdf shorts
+__global__ void __launch_bounds__(256) k_extract_tsdf(short* out, const short2* vol, size_t n) {
+	const size_t stride = (size_t) gridDim.x * blockDim.x;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = vol[i].x;
+}
+
+#endif
