@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — frames/s of the KinectFusion per-frame pipeline (preprocess -> track -> integrate ->
+raycast) on B200, through the C ABI of libkfb200.so (include/kfb200.h).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--volume 512]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A STEP is one 640x480 depth frame through the whole pipeline, driven exactly like
+kfusion/src/benchmark.cpp:125-150 drives `Kfusion`.  The workload is BASELINE.json configs[1]:
+the synthetic analytic-room sequence, 512^3 volume, 4.8 m, mu 0.1, pyramid 10,5,4, -r 1 -t 1.
+With W >= 4 the warm-up covers the reference's start-up frames 0-3 (untracked by construction,
+SURVEY §8a a18), so every timed frame is tracked + integrated + raycast.
+
+  value     whole-job frames/s with the uint16 sensor frames already resident in HBM
+  e2e       the same frames from pinned HOST memory through kfb_preprocess (H2D inside the timed
+            region) with the pose / ICP sums read back every frame (D2H inside)
+  roofline  the integrate kernel: algorithmic bytes (8*N_upd + 4*P per launch; N_upd
+            counted exactly by the kernel) / its CUDA-event time measured in the timed region
+  cpu_baseline  the unmodified reference C++ backend (oracle/_ref, OpenMP) or, where that was not
+            built, the plain-C restatement, timed on this box's host cores on a bounded sample
+
+N > 1: one process per GPU, one independent sequence per GPU (BASELINE configs[2]), no data-path
+collective; value = sum of frames / max-over-ranks time ("weak" scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "frames/sec end-to-end (640x480)"
+UNIT = "frames/s"
+W_IMG, H_IMG = 640, 480
+P_PIX = W_IMG * H_IMG
+MU = 0.1
+ICP_THRESHOLD = 1e-5
+PYRAMID = (10, 5, 4)
+VOLUME_DIM = 4.8
+
+
+def workload_name(vres: int) -> str:
+    which = {256: "configs[0]", 512: "configs[1]"}.get(vres, "configs[1] family")
+    return (f"{which}: synthetic analytic-room 640x480 .raw-format depth sequence, {vres}^3 short2 TSDF, 4.8 m, "
+            f"mu 0.1, pyramid 10,5,4, integration/tracking rate 1")
+
+
+def host_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = f"/tmp/kfb_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1]))
+                    mx.append(float(c[2]))
+                except ValueError:
+                    continue
+                for nm, v in zip(names, c[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# ----------------------------------------------------------------------------- CPU baseline
+def run_cpu_frames(depth, vres: int, n_warm: int, n_timed: int, budget_s: float | None):
+    """Drive the reference CPU backend over depth[0 : n_warm + n_timed]; returns
+    (frames timed, seconds, kind, cores, impl name).  Test-infrastructure code path: this is the one
+    place bench.py executes oracle/ as the thing measured (cpu_baseline / --impl reference)."""
+    from oracle import cpu_backend as cb
+    from slambench_b200 import synth
+
+    if os.path.exists(cb.REF_OMP_LIB):
+        lib, kind, cores = cb.REF_OMP_LIB, "reference", host_cores()
+    elif os.path.exists(cb.REF_LIB):
+        lib, kind, cores = cb.REF_LIB, "reference", 1
+    else:
+        cb.build_port()
+        lib, kind, cores = cb.PORT_LIB, "port", host_cores()   # the C restatement is built with -fopenmp too
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    be = cb.CpuKfusion(lib)
+    K = np.array(synth.K_DEFAULT, np.float32)
+    T0 = (np.array(synth.INIT_POS_FACTOR, np.float32) * np.float32(VOLUME_DIM)).astype(np.float32)
+    be.create((W_IMG, H_IMG), vres, VOLUME_DIM, T0, PYRAMID)
+    done, t_sum = 0, 0.0
+    try:
+        for f in range(min(len(depth), n_warm + n_timed)):
+            t0 = time.perf_counter()
+            be.preprocessing(depth[f])
+            be.tracking(K, ICP_THRESHOLD, 1, f)
+            be.integration(K, 1, MU, f)
+            be.raycasting(K, MU, f)
+            dt = time.perf_counter() - t0
+            if f >= n_warm:
+                done += 1
+                t_sum += dt
+                if budget_s is not None and t_sum > budget_s and done >= 4:
+                    break
+    finally:
+        be.destroy()
+    return done, t_sum, kind, cores, be.name
+
+
+def reference_arm(args, rank: int):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's cores."""
+    if rank != 0:
+        return
+    from slambench_b200 import synth
+
+    n = args.warmup + args.steps
+    depth, _ = synth.make_sequence(n, long_run=False if n <= 400 else None)
+    done, secs, kind, cores, name = run_cpu_frames(depth, args.volume, args.warmup, args.steps, None)
+    fps = done / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": done, "warmup": args.warmup,
+        "ms_per_step": 1e3 * secs / done, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": {"workload": workload_name(args.volume), "volume": args.volume, "backend": name},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"frames {args.warmup}..{args.warmup + done - 1} of the same sequence, whole pipeline per frame"},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------- B200 arm
+def b200_arm(args, rank: int, world: int, local_rank: int):
+    import torch
+
+    from slambench_b200 import kfusion as kf
+    from slambench_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libkfb200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    K = np.array(synth.K_DEFAULT, np.float32)
+    T0 = (np.array(synth.INIT_POS_FACTOR, np.float32) * np.float32(VOLUME_DIM)).astype(np.float32)
+    n = args.warmup + args.steps
+    # one independent sequence per GPU (seed = rank); deterministic, no RNG
+    depth_np, gt = synth.make_sequence(n, seed=rank % 8, long_run=False if n <= 400 else None)
+    host = torch.from_numpy(depth_np).pin_memory()                   # pinned host frames (e2e arm)
+    dev = host.to(f"cuda:{local_rank}", non_blocking=False)          # HBM-resident frames (value arm)
+    frame_bytes = W_IMG * H_IMG * 2
+
+    def run(resident: bool, time_mask: int):
+        """W warm-up frames, then exactly K timed frames.  Returns dict of measurements."""
+        with kf.Kfusion((W_IMG, H_IMG), args.volume, VOLUME_DIM, T0, PYRAMID, device=local_rank) as g:
+            stream = torch.cuda.ExternalStream(g.stream(), device=local_rank)
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+            def frame(f):
+                if resident:
+                    g.preprocessing_device(dev[f].data_ptr(), (W_IMG, H_IMG))
+                else:
+                    g.preprocessing(depth_np[f])          # numpy view of the pinned tensor's memory
+                tr = g.tracking(K, ICP_THRESHOLD, 1, f)
+                it = g.integration(K, 1, MU, f)
+                g.raycasting(K, MU, f)
+                return tr, it, g.getPose()                # pose is on the host when tracking returns
+
+            tracked = integrated = 0
+            for f in range(args.warmup):
+                frame(f)
+            g.synchroniseDevices()
+            g.enable_timing(time_mask)
+            g.reset_stats()
+            barrier()
+            clocks = ClockSampler(local_rank)
+            if time_mask and rank == 0:
+                clocks.start()
+            t0 = time.perf_counter()
+            ev0.record(stream)
+            for f in range(args.warmup, n):
+                tr, it, pose = frame(f)
+                tracked += tr
+                integrated += it
+            ev1.record(stream)
+            g.synchroniseDevices()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - t0
+            ck = clocks.stop() if (time_mask and rank == 0) else None
+            barrier()
+            ms = ev0.elapsed_time(ev1)
+            st = g.stats()
+            err = float(np.abs(pose[:3, 3] - gt[n - 1][:3, 3]).max())
+            return dict(ms=ms, wall_ms=wall * 1e3, st=st, tracked=tracked, integrated=integrated, err=err, clocks=ck)
+
+    # depth_np must alias the pinned buffer for the e2e arm
+    depth_np = host.numpy()
+    res = run(resident=True, time_mask=4)        # value: HBM-resident input; integrate timed with CUDA events
+    e2e = run(resident=False, time_mask=0)       # e2e: pinned host frames, H2D + D2H inside the timed region
+    diag = run(resident=True, time_mask=15) if rank == 0 and not args.no_breakdown else None
+
+    def reduce_max(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    ms = reduce_max(res["ms"])
+    ms_e2e = reduce_max(max(e2e["ms"], e2e["wall_ms"]))   # host-visible completion: the slower of device and wall time
+    launches = reduce_sum(float(res["st"]["kernel_launches"]))
+    all_tracked = reduce_sum(float(res["tracked"]))
+    K_steps = args.steps
+    value = world * K_steps / (ms * 1e-3)
+    e2e_value = world * K_steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        st = res["st"]
+        peak, peak_src = peaks()
+        n_int = max(1, int(st["frames_integrated"]))
+        alg_bytes = (8.0 * st["voxels_updated_total"] + 4.0 * P_PIX * n_int) / n_int
+        t_int_s = (st["ms_integrate"] / n_int) * 1e-3
+        achieved = alg_bytes / t_int_s / 1e9 if t_int_s > 0 else 0.0
+        full_sweep_bytes = 8.0 * args.volume ** 3 + 4.0 * P_PIX
+        roof = {
+            "bound": "hbm", "kernel": "k_integrate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": args.traffic_bytes, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": t_int_s * 1e6,
+            "n_upd_per_launch": st["voxels_updated_total"] / n_int,
+            "full_sweep_gbs": full_sweep_bytes / t_int_s / 1e9 if t_int_s > 0 else 0.0,
+            "launches_timed": n_int,
+        }
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_steps, "warmup": args.warmup,
+            "ms_per_step": ms / K_steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args.volume), "volume": args.volume, "image": [W_IMG, H_IMG],
+                       "frames": n, "parallelism": "1 sequence per GPU, no collective" if world > 1 else "single GPU",
+                       "l2": f"no flush: the {4 * args.volume ** 3 / 1e6:.0f} MB volume streamed every frame exceeds the 126 MB L2"
+                             if args.volume >= 512 else "no flush: volume fits L2 (the reference's own case); see --volume 512",
+                       "tracked_frames": int(all_tracked), "final_pose_err_m": res["err"]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": frame_bytes,
+                    "d2h_bytes_per_step": e2e["st"]["d2h_bytes"] / K_steps, "ms_per_step": ms_e2e / K_steps},
+            "gpu_launches": int(launches),
+            "clocks": res["clocks"],
+            "roofline": roof,
+        }
+        if diag is not None:
+            d = diag["st"]
+            line["stage_ms_per_frame"] = {
+                "preprocess": d["ms_preprocess"] / K_steps, "track": d["ms_track"] / K_steps,
+                "integrate": d["ms_integrate"] / max(1, d["frames_integrated"]), "raycast": d["ms_raycast"] / K_steps,
+                "icp_iterations": d["icp_iterations_total"] / K_steps, "launches": d["kernel_launches"] / K_steps,
+            }
+        if world == 1 and not args.no_cpu_baseline:
+            done, secs, kind, cores, name = run_cpu_frames(depth_np, args.volume, min(4, args.warmup), args.steps, args.cpu_budget)
+            line["cpu_baseline"] = {"value": done / secs, "unit": UNIT, "cores": cores, "kind": kind, "backend": name,
+                                    "sample": f"{done} frames (from frame {min(4, args.warmup)}) of the same sequence and volume, "
+                                              f"whole pipeline per frame, bounded to ~{args.cpu_budget:.0f} s"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=96)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--volume", type=int, default=512, help="volume resolution N (N^3 voxels); default = BASELINE configs[1]")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true", help="skip the extra per-stage timing pass")
+    ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes/launch of k_integrate from the ncu capture in profiles/")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one process per GPU)")
+    b200_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -148,7 +148,13 @@ int kfb_device_ptr(kfb_ctx* ctx, int which, int level, void** dev_ptr);
 /* ---- measurement ---- */
 int kfb_get_stats(kfb_ctx* ctx, kfb_stats* out);
 int kfb_reset_stats(kfb_ctx* ctx);
-int kfb_enable_timing(kfb_ctx* ctx, int on);
+/* CUDA-event timing of the stages; mask bits: 1 preprocess, 2 track, 4 integrate, 8 raycast (0 = off) */
+#define KFB_TIME_PREPROCESS 1
+#define KFB_TIME_TRACK 2
+#define KFB_TIME_INTEGRATE 4
+#define KFB_TIME_RAYCAST 8
+#define KFB_TIME_ALL 15
+int kfb_enable_timing(kfb_ctx* ctx, int mask);
 /* the CUDA stream all of this context's kernels are launched on (cudaStream_t as void*) */
 int kfb_stream(kfb_ctx* ctx, void** stream);
 

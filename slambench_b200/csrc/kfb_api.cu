@@ -94,21 +94,21 @@ struct kfb_ctx {
 	const void* reg_ptr[4]; size_t reg_bytes[4]; int n_reg;
 	// stats
 	kfb_stats st;
-	bool timing;
+	uint32_t timing;            // bitmask: 1 preprocess, 2 track, 4 integrate, 8 raycast
 	StageTimer t_pre, t_track, t_int, t_ray;
 };
 
 // ------------------------------------------------------------------------------------------
-static void timer_begin(kfb_ctx* c, StageTimer& t) {
-	if (!c->timing) return;
+static void timer_begin(kfb_ctx* c, StageTimer& t, uint32_t bit) {
+	if (!(c->timing & bit)) return;
 	EvPair p;
 	if (!t.pool.empty()) { p = t.pool.back(); t.pool.pop_back(); }
 	else { cudaEventCreate(&p.a); cudaEventCreate(&p.b); }
 	cudaEventRecord(p.a, c->stream);
 	t.pending.push_back(p);
 }
-static void timer_end(kfb_ctx* c, StageTimer& t) {
-	if (!c->timing) return;
+static void timer_end(kfb_ctx* c, StageTimer& t, uint32_t bit) {
+	if (!(c->timing & bit)) return;
 	cudaEventRecord(t.pending.back().b, c->stream);
 }
 static void timer_resolve(kfb_ctx* c, StageTimer& t) {
@@ -198,7 +198,7 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	if (c->z0 == 0 && c->z1 == 0) c->z1 = cfg->volume_res[2];
 	if (c->z1 > cfg->volume_res[2] || c->z0 >= c->z1) { delete c; return set_err(KFB_E_ARG, "bad z-slab [%u,%u)", cfg->slab_z0, cfg->slab_z1); }
 	c->slab_voxels = (size_t) cfg->volume_res[0] * cfg->volume_res[1] * (c->z1 - c->z0);
-	c->timing = false;
+	c->timing = 0;
 	c->rank = 0; c->world = 1; c->nccl_comm = nullptr;
 	c->n_reg = 0;
 	c->d_input = nullptr; c->input_bytes = 0; c->h_stage = nullptr; c->stage_bytes = 0;
@@ -318,7 +318,7 @@ int kfb_preprocess(kfb_ctx* c, const uint16_t* depth, uint32_t iw, uint32_t ih) 
 	if ((rc = check_ratio(c, iw, ih, &ratio))) return rc;
 	const size_t bytes = (size_t) iw * ih * sizeof(uint16_t);
 	if ((rc = ensure_input(c, bytes))) return rc;
-	timer_begin(c, c->t_pre);
+	timer_begin(c, c->t_pre, 1u);
 	// Is the caller's buffer already page-locked (ours, torch's pinned pool, or registered before)?
 	bool pinned = false;
 	for (int i = 0; i < c->n_reg; ++i) if (c->reg_ptr[i] == depth && c->reg_bytes[i] >= bytes) pinned = true;
@@ -348,7 +348,7 @@ int kfb_preprocess(kfb_ctx* c, const uint16_t* depth, uint32_t iw, uint32_t ih) 
 	}
 	c->st.h2d_bytes += bytes;
 	rc = launch_preprocess(c, c->d_input, iw, ratio);
-	timer_end(c, c->t_pre);
+	timer_end(c, c->t_pre, 1u);
 	return rc;
 }
 
@@ -357,9 +357,9 @@ int kfb_preprocess_device(kfb_ctx* c, const uint16_t* d_depth, uint32_t iw, uint
 	CK(cudaSetDevice(c->device));
 	int ratio, rc;
 	if ((rc = check_ratio(c, iw, ih, &ratio))) return rc;
-	timer_begin(c, c->t_pre);
+	timer_begin(c, c->t_pre, 1u);
 	rc = launch_preprocess(c, d_depth, iw, ratio);
-	timer_end(c, c->t_pre);
+	timer_end(c, c->t_pre, 1u);
 	return rc;
 }
 
@@ -453,7 +453,7 @@ int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracki
 	if (tracked) *tracked = 0;
 	if (tracking_rate == 0) return set_err(KFB_E_ARG, "tracking_rate must be > 0");
 	if (frame % tracking_rate != 0) return 0;                       // cpp/kernels.cpp:927
-	timer_begin(c, c->t_track);
+	timer_begin(c, c->t_track, 2u);
 	int rc = launch_pyramid(c, k);                                  // :931-945
 	if (rc) return rc;
 	memcpy(c->oldPose, c->pose, sizeof c->pose);                    // :947
@@ -470,7 +470,7 @@ int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracki
 			if (hm_update_pose(c->pose, c->reduction, icp_threshold)) break;
 		}
 	}
-	timer_end(c, c->t_track);
+	timer_end(c, c->t_track, 2u);
 	c->st.icp_iterations_last = iters;
 	c->st.icp_iterations_total += iters;
 	const int ok = hm_check_pose(c->pose, c->oldPose, c->reduction, c->cw, c->ch, c_track_threshold);  // :968
@@ -510,9 +510,9 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 
 int kfb_k_integrate(kfb_ctx* c, const float invTrack[16], const float K[16], float mu, float maxweight) {
 	CK(cudaSetDevice(c->device));
-	timer_begin(c, c->t_int);
+	timer_begin(c, c->t_int, 4u);
 	int rc = launch_integrate(c, invTrack, K, mu, maxweight);
-	timer_end(c, c->t_int);
+	timer_end(c, c->t_int, 4u);
 	return rc;
 }
 
@@ -525,9 +525,9 @@ int kfb_integrate(kfb_ctx* c, const float k[4], uint32_t integration_rate, float
 		float inv[16], K[16];
 		hm_inverse4(inv, c->pose);
 		hm_camera_matrix(K, k);
-		timer_begin(c, c->t_int);
+		timer_begin(c, c->t_int, 4u);
 		int rc = launch_integrate(c, inv, K, mu, c_maxweight);                                             // :995-996
-		timer_end(c, c->t_int);
+		timer_end(c, c->t_int, 4u);
 		if (rc) return rc;
 		doIntegrate = 1;
 	} else doIntegrate = 0;
@@ -553,9 +553,9 @@ static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP
 
 int kfb_k_raycast(kfb_ctx* c, const float view[16], float nearP, float farP, float step, float largestep) {
 	CK(cudaSetDevice(c->device));
-	timer_begin(c, c->t_ray);
+	timer_begin(c, c->t_ray, 8u);
 	int rc = launch_raycast(c, view, nearP, farP, step, largestep);
-	timer_end(c, c->t_ray);
+	timer_end(c, c->t_ray, 8u);
 	return rc;
 }
 
@@ -567,9 +567,9 @@ int kfb_raycast(kfb_ctx* c, const float k[4], float mu, uint32_t frame) {
 		float invK[16], view[16];
 		hm_inverse_camera_matrix(invK, k);
 		hm_matmul4(view, c->raycastPose, invK);
-		timer_begin(c, c->t_ray);
+		timer_begin(c, c->t_ray, 8u);
 		int rc = launch_raycast(c, view, c_nearPlane, c_farPlane, c->step, 0.75f * mu);   // :979-981
-		timer_end(c, c->t_ray);
+		timer_end(c, c->t_ray, 8u);
 		return rc;
 	}
 	return 0;
@@ -731,7 +731,7 @@ int kfb_write_buffer(kfb_ctx* c, int which, int level, const void* src, size_t b
 }
 
 // -------------------------------------------------------------------------- measurement
-int kfb_enable_timing(kfb_ctx* c, int on) { c->timing = on != 0; return 0; }
+int kfb_enable_timing(kfb_ctx* c, int mask) { c->timing = (uint32_t) mask; return 0; }
 int kfb_reset_stats(kfb_ctx* c) {
 	CK(cudaSetDevice(c->device));
 	CK(cudaStreamSynchronize(c->stream));

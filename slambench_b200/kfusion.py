@@ -328,8 +328,10 @@ class Kfusion:
         self._check(self.lib.kfb_stream(self._h, C.byref(s)))
         return s.value or 0
 
-    def enable_timing(self, on: bool = True):
-        self._check(self.lib.kfb_enable_timing(self._h, C.c_int(int(on))))
+    def enable_timing(self, on=True):
+        """`on`: True/False for all stages, or a bitmask (1 preprocess, 2 track, 4 integrate, 8 raycast)."""
+        mask = (15 if on else 0) if isinstance(on, bool) else int(on)
+        self._check(self.lib.kfb_enable_timing(self._h, C.c_int(mask)))
 
     def reset_stats(self):
         self._check(self.lib.kfb_reset_stats(self._h))
