@@ -79,10 +79,15 @@ struct kfb_ctx {
 	double* d_partials;
 	unsigned int* d_counter;
 	float* d_out32;
-	float* h_out32;             // mapped pinned: [0..31] result, [32] seq flag
+	float* h_out32;             // mapped pinned: [0..31] result, [32] seq flag, [48..63] pose, [64] iterations
+	IcpState* d_icp;            // device-resident ICP loop state
+	IcpState* h_icp_stage;      // pinned staging for the per-frame initial state
 	float* h_out32_dev;
 	uint32_t seq;
 	unsigned long long* d_nupd; // NUPD_SLOTS per-integrate counters
+	unsigned int* d_dmax;       // two slots: bit pattern of max(floatDepth), written by preprocess (ping-pong)
+	int dmax_slot;              // slot holding the max of the CURRENT floatDepth, -1 = unknown
+	uint64_t preprocess_count;
 	uint64_t integrate_count;
 	uchar4* d_render; size_t render_bytes;
 	// multi-GPU
@@ -231,11 +236,16 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	CK(cudaMemsetAsync(c->d_counter, 0, sizeof(unsigned int), c->stream));
 	CK(cudaMalloc(&c->d_out32, 32 * sizeof(float)));
 	CK(cudaMemsetAsync(c->d_out32, 0, 32 * sizeof(float), c->stream));
-	CK(cudaHostAlloc(&c->h_out32, 64 * sizeof(float), cudaHostAllocMapped));
-	memset(c->h_out32, 0, 64 * sizeof(float));
+	CK(cudaHostAlloc(&c->h_out32, 128 * sizeof(float), cudaHostAllocMapped));
+	memset(c->h_out32, 0, 128 * sizeof(float));
+	CK(cudaMalloc(&c->d_icp, sizeof(IcpState)));
+	CK(cudaMemsetAsync(c->d_icp, 0, sizeof(IcpState), c->stream));
+	CK(cudaHostAlloc(&c->h_icp_stage, sizeof(IcpState), cudaHostAllocDefault));
 	CK(cudaHostGetDevicePointer(&c->h_out32_dev, c->h_out32, 0));
 	CK(cudaMalloc(&c->d_nupd, NUPD_SLOTS * sizeof(unsigned long long)));
-	CK(cudaMemsetAsync(c->d_nupd, 0, NUPD_SLOTS * sizeof(unsigned long long), c->stream));
+	CK(cudaMalloc(&c->d_dmax, 2 * sizeof(unsigned int)));
+	CK(cudaMemsetAsync(c->d_dmax, 0, 2 * sizeof(unsigned int), c->stream));
+	c->dmax_slot = -1; c->preprocess_count = 0;
 	// single-slab view by default
 	memset(&c->view_all, 0, sizeof c->view_all);
 	c->view_all.n_slabs = 1;
@@ -259,8 +269,8 @@ int kfb_destroy(kfb_ctx* c) {
 	for (int i = 0; i < KFB_MAX_SLABS; ++i) if (c->peer_ptrs[i]) cudaIpcCloseMemHandle(c->peer_ptrs[i]);
 	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_floatDepth);
 	for (int l = 0; l < c->levels; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
-	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd);
-	cudaFreeHost(c->h_out32);
+	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax);
+	cudaFreeHost(c->h_out32); cudaFree(c->d_icp); cudaFreeHost(c->h_icp_stage);
 	if (c->d_input) cudaFree(c->d_input);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->d_render) cudaFree(c->d_render);
@@ -298,7 +308,10 @@ static int launch_preprocess(kfb_ctx* c, const uint16_t* d_in, uint32_t iw, int 
 	Gauss5 g;
 	memcpy(g.g, c->gaussian, sizeof g.g);
 	dim3 grid((c->cw + PP_BX - 1) / PP_BX, (c->ch + PP_BY - 1) / PP_BY), block(PP_BX, PP_BY);
-	k_mm2m_bilateral<<<grid, block, 0, c->stream>>>(d_in, iw, ratio, c->d_floatDepth, c->d_scaled[0], c->cw, c->ch, g, c_e_delta);
+	const int slot = (int) (c->preprocess_count++ & 1);
+	k_mm2m_bilateral<<<grid, block, 0, c->stream>>>(d_in, iw, ratio, c->d_floatDepth, c->d_scaled[0], c->cw, c->ch, g, c_e_delta,
+			c->d_dmax + slot, c->d_dmax + (slot ^ 1));
+	c->dmax_slot = slot;
 	LAUNCHED(c);
 	CK(cudaGetLastError());
 	return 0;
@@ -396,7 +409,24 @@ static uint32_t track_blocks(uint32_t npx) {
 }
 
 // one fused track+reduce launch; result lands in c->h_out32 (mapped) when wait == true
-static int launch_track(kfb_ctx* c, int level, const float* T, const float* V, float dist, float nthr, bool wait) {
+static int wait_seq(kfb_ctx* c, uint32_t seq) {
+	volatile uint32_t* flag = (volatile uint32_t*) (c->h_out32 + 32);
+	// spin on the mapped flag; fall back to a stream query so a faulted kernel cannot hang us
+	uint64_t spins = 0;
+	while (*flag != seq) {
+		if ((++spins & 0xfffff) == 0) {
+			cudaError_t q = cudaStreamQuery(c->stream);
+			if (q != cudaErrorNotReady && q != cudaSuccess) return set_err(KFB_E_CUDA, "track kernel failed: %s", cudaGetErrorString(q));
+			if (q == cudaSuccess && *flag != seq) return set_err(KFB_E_CUDA, "track kernel finished without publishing its result");
+		}
+	}
+	__sync_synchronize();
+	return 0;
+}
+
+// icp_mode: 0 = host loop (result published every launch), 1 = device-resident loop, 2 = same and last launch of the frame
+static int launch_track(kfb_ctx* c, int level, const float* T, const float* V, float dist, float nthr, bool wait, int icp_mode = 0,
+		float icp_threshold = 0.f) {
 	TrackParams p;
 	memset(&p, 0, sizeof p);
 	p.inV = c->d_inV[level]; p.inN = c->d_inN[level];
@@ -409,24 +439,20 @@ static int launch_track(kfb_ctx* c, int level, const float* T, const float* V, f
 	p.partials = c->d_partials; p.counter = c->d_counter; p.out32 = c->d_out32;
 	p.out32_host = c->h_out32_dev;
 	p.seq_host = (volatile uint32_t*) (c->h_out32_dev + 32);
-	p.seq = ++c->seq;
+	p.seq = (icp_mode == 1) ? c->seq : ++c->seq;
 	p.status = (c->cfg.flags & KFB_FLAG_TRACK_STATUS) ? c->d_status : nullptr;
+	p.icp = nullptr; p.level = level; p.is_final = 0; p.icp_threshold = icp_threshold; p.pose_host = c->h_out32_dev + 48;
+	if (icp_mode) {
+		p.icp = c->d_icp; p.is_final = (icp_mode == 2);
+		p.pose_dev = c->d_icp->pose; p.view_dev = c->d_icp->view;
+	}
 	const uint32_t blocks = track_blocks(p.w * (p.row1 - p.row0));
 	k_track_reduce<<<blocks, TR_THREADS, 0, c->stream>>>(p);
 	LAUNCHED(c);
 	CK(cudaGetLastError());
 	if (wait) {
-		volatile uint32_t* flag = (volatile uint32_t*) (c->h_out32 + 32);
-		// spin on the mapped flag; fall back to a stream query so a faulted kernel cannot hang us
-		uint64_t spins = 0;
-		while (*flag != p.seq) {
-			if ((++spins & 0xfffff) == 0) {
-				cudaError_t q = cudaStreamQuery(c->stream);
-				if (q != cudaErrorNotReady && q != cudaSuccess) return set_err(KFB_E_CUDA, "track kernel failed: %s", cudaGetErrorString(q));
-				if (q == cudaSuccess && *flag != p.seq) return set_err(KFB_E_CUDA, "track kernel finished without publishing its result");
-			}
-		}
-		__sync_synchronize();
+		int rc = wait_seq(c, p.seq);
+		if (rc) return rc;
 		memcpy(c->reduction, c->h_out32, 32 * sizeof(float));
 		c->st.d2h_bytes += 32 * sizeof(float);
 	}
@@ -462,12 +488,41 @@ int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracki
 	hm_inverse4(invRP, c->raycastPose);
 	hm_matmul4(projectReference, K, invRP);                         // :948
 	uint64_t iters = 0;
-	for (int level = c->levels - 1; level >= 0; --level) {         // :950-967
-		for (int i = 0; i < c->cfg.iterations[level]; ++i) {
-			rc = launch_track(c, level, c->pose, projectReference, c_dist_threshold, c_normal_threshold, true);
+	if (c->cfg.flags & KFB_FLAG_ICP_HOST_SOLVE) {
+		for (int level = c->levels - 1; level >= 0; --level) {         // :950-967
+			for (int i = 0; i < c->cfg.iterations[level]; ++i) {
+				rc = launch_track(c, level, c->pose, projectReference, c_dist_threshold, c_normal_threshold, true);
+				if (rc) return rc;
+				++iters;
+				if (hm_update_pose(c->pose, c->reduction, icp_threshold)) break;
+			}
+		}
+	} else {
+		// device-resident loop: the whole schedule is enqueued; solve, pose update and the per-level
+		// `break` happen in the last CTA of each launch; ONE host wait per frame
+		int total = 0, last_level = -1;
+		for (int level = 0; level < c->levels; ++level) if (c->cfg.iterations[level] > 0) { total += c->cfg.iterations[level]; if (last_level < 0) last_level = level; }
+		if (total > 0) {
+			IcpState* st = c->h_icp_stage;
+			memcpy(st->pose, c->pose, sizeof st->pose);
+			memcpy(st->view, projectReference, sizeof st->view);
+			memset(st->done, 0, sizeof st->done);
+			st->iters = 0;
+			CK(cudaMemcpyAsync(c->d_icp, st, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
+			c->st.h2d_bytes += sizeof(IcpState);
+			++c->seq;
+			for (int level = c->levels - 1; level >= 0; --level)
+				for (int i = 0; i < c->cfg.iterations[level]; ++i) {
+					const bool fin = (level == last_level) && (i == c->cfg.iterations[level] - 1);
+					rc = launch_track(c, level, c->pose, projectReference, c_dist_threshold, c_normal_threshold, false, fin ? 2 : 1, icp_threshold);
+					if (rc) return rc;
+				}
+			rc = wait_seq(c, c->seq);
 			if (rc) return rc;
-			++iters;
-			if (hm_update_pose(c->pose, c->reduction, icp_threshold)) break;
+			memcpy(c->reduction, c->h_out32, 32 * sizeof(float));
+			memcpy(c->pose, c->h_out32 + 48, 16 * sizeof(float));
+			iters = *(volatile uint32_t*) (c->h_out32 + 64);
+			c->st.d2h_bytes += (32 + 16 + 1) * sizeof(float);
 		}
 	}
 	timer_end(c, c->t_track, 2u);
@@ -488,6 +543,8 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	p.depth = c->d_floatDepth; p.dw = c->cw; p.dh = c->ch;
 	p.invTrack = toMat(invTrack); p.K = toMat(K);
 	p.mu = mu; p.maxweight = maxweight;
+	p.cull = (c->cfg.flags & KFB_FLAG_INTEGRATE_NO_CULL) ? 0 : 1;
+	p.dmax = (c->dmax_slot >= 0) ? reinterpret_cast<const float*>(c->d_dmax + c->dmax_slot) : nullptr;
 	const uint32_t slot = (uint32_t) (c->integrate_count % NUPD_SLOTS);
 	if (c->integrate_count >= NUPD_SLOTS) CK(cudaMemsetAsync(c->d_nupd + slot, 0, sizeof(unsigned long long), c->stream));
 	p.n_upd = c->d_nupd + slot;
@@ -725,6 +782,7 @@ int kfb_write_buffer(kfb_ctx* c, int which, int level, const void* src, size_t b
 	if (bytes > b) return set_err(KFB_E_ARG, "write of %zu bytes into a %zu-byte buffer", bytes, b);
 	CK(cudaSetDevice(c->device));
 	if (host) { memcpy(p, src, bytes); return 0; }
+	if (which == KFB_BUF_FLOATDEPTH) c->dmax_slot = -1;   // the cached max no longer describes this image
 	CK(cudaStreamSynchronize(c->stream));
 	CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
 	return 0;

@@ -114,6 +114,76 @@ KFB_HM void hm_solve6(double* x6, const float* vals27) {
 	for (int r = 0; r < 6; ++r) { double s = 0; for (int i = 0; i < 6; ++i) s += V[r][i] * y[i]; x6[r] = s; }
 }
 
+// Fast path of the same solve for the device-resident ICP loop.  For a symmetric positive-definite
+// JtJ whose condition number is certified below the reference's pseudo-inverse cut-off
+// (cond <= trace(C) * trace(C^-1) < 1e6  =>  every singular value satisfies sigma * 1e6 > sigma_max
+// => GR_SVD::backsub keeps them all => x = C^-1 b), a Cholesky solve in double gives the same x to
+// ~cond * 1e-16.  Returns 0 (caller falls back to hm_solve6) when the certificate fails: not
+// positive definite (start-up frames: C == 0), NaN, or possibly ill-conditioned.
+KFB_HM int hm_solve6_chol(double* x6, const float* vals27) {
+	double b[6], C[6][6], L[6][6], M[6][6];
+#pragma unroll
+	for (int i = 0; i < 6; ++i) b[i] = vals27[i];
+	{
+		int idx = 6;
+#pragma unroll
+		for (int r = 0; r < 6; ++r)
+#pragma unroll
+			for (int c = r; c < 6; ++c) { C[r][c] = vals27[idx++]; C[c][r] = C[r][c]; }
+	}
+	double trC = 0;
+#pragma unroll
+	for (int i = 0; i < 6; ++i) trC += C[i][i];
+#pragma unroll
+	for (int j = 0; j < 6; ++j) {
+		double s = C[j][j];
+#pragma unroll
+		for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+		if (!(s > 0)) return 0;
+		const double d = sqrt(s), inv = 1.0 / d;
+		L[j][j] = d;
+#pragma unroll
+		for (int i = j + 1; i < 6; ++i) {
+			double t = C[i][j];
+#pragma unroll
+			for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
+			L[i][j] = t * inv;
+		}
+	}
+	// M = L^-1 (lower triangular); trace(C^-1) = ||M||_F^2
+	double trInv = 0;
+#pragma unroll
+	for (int j = 0; j < 6; ++j) {
+		M[j][j] = 1.0 / L[j][j];
+		trInv += M[j][j] * M[j][j];
+#pragma unroll
+		for (int i = j + 1; i < 6; ++i) {
+			double t = 0;
+#pragma unroll
+			for (int k = j; k < i; ++k) t -= L[i][k] * M[k][j];
+			M[i][j] = t / L[i][i];
+			trInv += M[i][j] * M[i][j];
+		}
+	}
+	if (!(trC * trInv < 0.99e6)) return 0;
+	double y[6];
+#pragma unroll
+	for (int i = 0; i < 6; ++i) {
+		double t = 0;
+#pragma unroll
+		for (int j = 0; j <= i; ++j) t += M[i][j] * b[j];
+		y[i] = t;
+	}
+#pragma unroll
+	for (int j = 0; j < 6; ++j) {
+		double t = 0;
+#pragma unroll
+		for (int i = j; i < 6; ++i) t += M[i][j] * y[i];
+		x6[j] = t;
+	}
+	return 1;
+}
+
 // TooN::SE3<double>::exp followed by toMatrix4 (commons.h:406-412)
 KFB_HM void hm_se3_exp(float* out16, const double* mu) {
 	const double w0 = mu[3], w1 = mu[4], w2 = mu[5], t0 = mu[0], t1 = mu[1], t2 = mu[2];
@@ -159,6 +229,17 @@ KFB_HM void hm_se3_exp(float* out16, const double* mu) {
 KFB_HM int hm_update_pose(float* pose, const float* red, float icp_threshold) {
 	double x[6];
 	hm_solve6(x, red + 1);
+	float d[16];
+	hm_se3_exp(d, x);
+	hm_matmul4(pose, d, pose);
+	double n = 0;
+	for (int i = 0; i < 6; ++i) n += x[i] * x[i];
+	return sqrt(n) < (double) icp_threshold;
+}
+// same, with the certified Cholesky fast path (device-resident ICP loop)
+KFB_HM int hm_update_pose_fast(float* pose, const float* red, float icp_threshold) {
+	double x[6];
+	if (!hm_solve6_chol(x, red + 1)) hm_solve6(x, red + 1);
 	float d[16];
 	hm_se3_exp(d, x);
 	hm_matmul4(pose, d, pose);

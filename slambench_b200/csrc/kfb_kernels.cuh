@@ -36,8 +36,10 @@ struct Gauss5 { float g[5]; };
 #define PP_BY 8
 #define PP_R 2
 __global__ void __launch_bounds__(PP_BX* PP_BY) k_mm2m_bilateral(const uint16_t* __restrict__ in, uint32_t iw, int ratio,
-		float* __restrict__ raw, float* __restrict__ filt, uint32_t w, uint32_t h, Gauss5 gs, float e_d) {
+		float* __restrict__ raw, float* __restrict__ filt, uint32_t w, uint32_t h, Gauss5 gs, float e_d,
+		unsigned int* __restrict__ dmax_bits, unsigned int* __restrict__ dmax_next) {
 	__shared__ float tile[PP_BY + 2 * PP_R][PP_BX + 2 * PP_R + 1];
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) *dmax_next = 0u;  // re-arm the other slot
 	const int x0 = blockIdx.x * PP_BX, y0 = blockIdx.y * PP_BY;
 	const int tid = threadIdx.y * PP_BX + threadIdx.x;
 	for (int i = tid; i < (PP_BY + 2 * PP_R) * (PP_BX + 2 * PP_R); i += PP_BX * PP_BY) {
@@ -48,8 +50,14 @@ __global__ void __launch_bounds__(PP_BX* PP_BY) k_mm2m_bilateral(const uint16_t*
 	}
 	__syncthreads();
 	const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-	if (x >= (int) w || y >= (int) h) return;
+	const bool inside = x < (int) w && y < (int) h;
 	const float center = tile[threadIdx.y + PP_R][threadIdx.x + PP_R];
+	// max of the raw depth image (non-negative floats order like their bit patterns): integrate's far cull
+	{
+		const unsigned int m = __reduce_max_sync(0xffffffffu, inside ? __float_as_uint(center) : 0u);
+		if (threadIdx.x == 0 && m) atomicMax(dmax_bits, m);
+	}
+	if (!inside) return;
 	const size_t pos = (size_t) x + (size_t) y * w;
 	raw[pos] = center;
 	if (center == 0) { filt[pos] = 0; return; }
@@ -159,6 +167,15 @@ __global__ void __launch_bounds__(256) k_pyramid(PyrParams p) {
 #define TR_THREADS 256
 #define TR_MAX_BLOCKS 1184  // 148 SMs x 8
 
+// device-resident ICP loop state (one per context): the whole level/iteration schedule of
+// Kfusion::tracking (cpp/kernels.cpp:950-967) is enqueued up front; each launch first looks here.
+struct IcpState {
+	float pose[16];          // current estimate, updated by the last CTA of every active iteration (:963)
+	float view[16];          // projectReference (:948), constant during a frame
+	int done[8];             // level converged: updatePoseKernel returned true => `break` (:963-964)
+	unsigned int iters;      // active iterations so far
+};
+
 struct TrackParams {
 	const float* inV; const float* inN;     // packed float3[w*h] of this level
 	const float* refV; const float* refN;   // packed float3[rw*rh] (raycast maps, world frame)
@@ -173,7 +190,25 @@ struct TrackParams {
 	float* out32;                           // device result
 	float* out32_host; volatile uint32_t* seq_host; uint32_t seq;  // optional mapped-host mirror + sequence flag
 	int8_t* status;                         // optional per-pixel result plane (stride rw), for renderTrack
+	IcpState* icp;                          // device-resident loop (nullptr: one launch per host iteration)
+	int level, is_final;
+	float icp_threshold;
+	float* pose_host;                       // mapped-host mirror of icp->pose [16] followed by iters [1]
 };
+
+// 6x6 solve + SE3 exp + pose composition by ONE thread of the last CTA (updatePoseKernel, :759-775)
+__device__ __noinline__ void icp_update_pose(const TrackParams& p, const float* red32) {
+	float pose[16];
+#pragma unroll
+	for (int i = 0; i < 16; ++i) pose[i] = p.icp->pose[i];
+	const int conv = hm_update_pose_fast(pose, red32, p.icp_threshold);
+#pragma unroll
+	for (int i = 0; i < 16; ++i) { p.icp->pose[i] = pose[i]; p.pose_host[i] = pose[i]; }
+	if (conv) p.icp->done[p.level] = 1;
+	const unsigned int it = p.icp->iters + 1;
+	p.icp->iters = it;
+	reinterpret_cast<volatile unsigned int*>(p.pose_host)[16] = it;
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -184,8 +219,16 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 __global__ void __launch_bounds__(TR_THREADS) k_track_reduce(TrackParams p) {
 	__shared__ double sm[TR_THREADS / 32][32];
+	__shared__ float red32[32];
 	__shared__ bool is_last;
 	Mat4 T, V;
+	if (p.icp && p.icp->done[p.level]) {
+		// this level already converged: the reference's `break`.  The last launch of the frame still
+		// publishes the sequence number the host is waiting for (results were published by the last
+		// active iteration, a kernel boundary ago).
+		if (p.is_final && blockIdx.x == 0 && threadIdx.x == 0 && p.seq_host) *p.seq_host = p.seq;
+		return;
+	}
 	if (p.pose_dev) {
 #pragma unroll
 		for (int i = 0; i < 16; ++i) { T.m[i] = p.pose_dev[i]; V.m[i] = p.view_dev[i]; }
@@ -294,8 +337,13 @@ __global__ void __launch_bounds__(TR_THREADS) k_track_reduce(TrackParams p) {
 		p.out32[lane] = r;
 		if (p.out32_host) p.out32_host[lane] = r;
 		if (lane == 0) *p.counter = 0;  // re-arm for the next launch
+		if (p.icp) {
+			red32[lane] = r;
+			__syncwarp();
+			if (lane == 0) icp_update_pose(p, red32);
+		}
 		__syncwarp();
-		if (p.seq_host) {
+		if (p.seq_host && (!p.icp || p.is_final)) {
 			__threadfence_system();
 			if (lane == 0) *p.seq_host = p.seq;
 		}
@@ -307,63 +355,160 @@ __global__ void __launch_bounds__(TR_THREADS) k_track_reduce(TrackParams p) {
 // project into the depth image.  The reference walks each (x,y) column from z = 0 and
 // advances `pos` / `cameraX` by REPEATED fp32 addition; reproducing those exact values is
 // what keeps every voxel bit-identical (recomputing pos0 + z*delta is off by several LSB,
-// SURVEY §7).  A thread owns one column and a z-chunk; it first replays the additions up
-// to its first z (6 independent FADD chains, no memory traffic), then streams its chunk.
-// x is the fastest thread index, so each warp touches 128 contiguous bytes per z-slice.
-// The kernel is launched on the slab [z_begin, z_end) this context owns; `vol` points at
-// the slab's first voxel.  N_upd (voxels actually updated) is counted exactly.
+// SURVEY §7).  Only ~8 % of the voxels are updated by a frame, and memory is touched for
+// those alone, so the cost that matters is DECIDING, for the other 92 %, that nothing
+// happens.  Three layers keep that cheap without changing a single result:
+//   1. per column, a conservative z-interval [za, zb) outside which the voxel provably fails
+//      the reference's `pos.z < 1e-4` / pixel-bounds tests (closed form on the un-rounded
+//      line, widened by a bound on the accumulated rounding error); a warp (32 x-adjacent
+//      columns -> 128 contiguous bytes per z-slice) takes the union of its lanes' intervals;
+//   2. the additions up to the interval start are REPLAYED in registers (6 independent FADD
+//      chains, no memory traffic, no tests) so the first visited voxel sees the reference's
+//      exact accumulated values;
+//   3. inside the interval the pixel is first located with an approximate division; only when
+//      the quotient is within 1e-3 of an integer (a pixel edge or the image border) is the
+//      IEEE division executed.  `e = depth - cameraX.z` then decides exactly, by monotonicity
+//      of correctly-rounded * and / and lambda = sqrt(1 + ..) >= 1:  e > mu  =>  sdf == 1;
+//      e < -mu  =>  no update;  otherwise the reference's full sqrt/division expression runs.
+// The kernel is launched on the slab [z_begin, z_end) this context owns; `vol` points at the
+// slab's first voxel.  N_upd (voxels actually updated) is counted exactly.
 // ------------------------------------------------------------------------------------------
+#define INT_U 8
 struct IntegrateParams {
 	short2* vol;
 	uint32_t sx, sy, sz;       // full volume resolution
 	float dx, dy, dz;          // volume dimensions (metres)
 	uint32_t z_begin, z_end;   // slab owned by this context
-	uint32_t zchunk;           // z-steps per thread
+	uint32_t zchunk;           // z-steps per blockIdx.z
 	const float* depth; uint32_t dw, dh;
 	Mat4 invTrack, K;
 	float mu, maxweight;
+	const float* dmax;         // optional: max of the depth image (device scalar); nullptr = unknown
+	int cull;                  // 0 = visit every voxel (debug / A-B), 1 = interval + fast tests
 	unsigned long long* n_upd;
 };
 
+// tighten [tlo, thi] with the constraint a + b*t >= -s (NaNs never tighten)
+__device__ __forceinline__ void clip_line(float a, float b, float s, float& tlo, float& thi) {
+	const float r = (-s - a) / b;   // b == 0 -> +-inf or NaN, handled below
+	if (b > 0.f) { if (r > tlo) tlo = r; }
+	else if (b < 0.f) { if (r < thi) thi = r; }
+	else if (a < -s) { tlo = 1.f; thi = 0.f; }
+}
+
 __global__ void __launch_bounds__(256) k_integrate(IntegrateParams p) {
-	const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;
+	const uint32_t x = blockIdx.x * 32 + threadIdx.x;
+	const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;   // warp-uniform
 	const uint32_t zs = p.z_begin + blockIdx.z * p.zchunk;
 	const uint32_t ze = min(zs + p.zchunk, p.z_end);
+	const bool valid = x < p.sx && y < p.sy && zs < ze;
 	unsigned int updated = 0;
-	if (x < p.sx && y < p.sy && zs < ze) {
-		const float3 delta = mat_rotate(p.invTrack, f3(0, 0, p.dz / (float) p.sz));
-		const float3 cameraDelta = mat_rotate(p.K, delta);
-		// Volume::pos (commons.h:186-189) at z = 0
-		float3 pos = mat_point(p.invTrack, f3(((float) x + 0.5f) * p.dx / (float) p.sx, ((float) y + 0.5f) * p.dy / (float) p.sy,
-				(0 + 0.5f) * p.dz / (float) p.sz));
-		float3 cameraX = mat_point(p.K, pos);
-		for (uint32_t z = 0; z < zs; ++z) { pos = pos + delta; cameraX = cameraX + cameraDelta; }
+
+	const float3 delta = mat_rotate(p.invTrack, f3(0, 0, p.dz / (float) p.sz));
+	const float3 cameraDelta = mat_rotate(p.K, delta);
+	// Volume::pos (commons.h:186-189) at z = 0
+	float3 pos = mat_point(p.invTrack, f3(((float) x + 0.5f) * p.dx / (float) p.sx, ((float) y + 0.5f) * p.dy / (float) p.sy,
+			(0 + 0.5f) * p.dz / (float) p.sz));
+	float3 cameraX = mat_point(p.K, pos);
+	const float dwm1 = (float) (p.dw - 1), dhm1 = (float) (p.dh - 1);
+
+	int za = (int) zs, zb = (int) ze;
+	if (!valid) { za = 0x7fffffff; zb = 0; }
+	else if (p.cull) {
+		// conservative interval on the un-rounded line; slack = bound on the accumulated rounding error
+		const float n = (float) p.sz;
+		const float Mx = kmaxf(fabsf(cameraX.x), fabsf(cameraX.x + n * cameraDelta.x));
+		const float My = kmaxf(fabsf(cameraX.y), fabsf(cameraX.y + n * cameraDelta.y));
+		const float Mz = kmaxf(fabsf(cameraX.z), fabsf(cameraX.z + n * cameraDelta.z));
+		const float Mp = kmaxf(fabsf(pos.z), fabsf(pos.z + n * delta.z));
+		const float eps = (n + 64.f) * 2.3841858e-7f;   // (N + 64) * 2^-22: > 2x the worst-case drift of N additions
+		const float wq = dwm1 - 0.5f, hq = dhm1 - 0.5f;
+		float tlo = -1e9f, thi = 1e9f;
+		clip_line(pos.z - 0.0001f, delta.z, eps * Mp, tlo, thi);                                                   // pos.z >= 1e-4
+		clip_line(cameraX.x + 0.5f * cameraX.z, cameraDelta.x + 0.5f * cameraDelta.z, eps * (Mx + Mz), tlo, thi);   // px >= 0
+		clip_line(wq * cameraX.z - cameraX.x, wq * cameraDelta.z - cameraDelta.x, eps * (Mx + (wq + 2.f) * Mz), tlo, thi);  // px <= w-1
+		clip_line(cameraX.y + 0.5f * cameraX.z, cameraDelta.y + 0.5f * cameraDelta.z, eps * (My + Mz), tlo, thi);   // py >= 0
+		clip_line(hq * cameraX.z - cameraX.y, hq * cameraDelta.z - cameraDelta.y, eps * (My + (hq + 2.f) * Mz), tlo, thi);  // py <= h-1
+		if (p.dmax) {
+			// no update unless depth - cameraX.z > -mu  (lambda >= 1)  =>  cameraX.z < max(depth) + mu
+			const float far = *p.dmax + p.mu;
+			if (far == far) clip_line(far - cameraX.z, -cameraDelta.z, eps * Mz + 1e-6f * fabsf(far), tlo, thi);
+		}
+		if (tlo > thi) { za = 0x7fffffff; zb = 0; }
+		else {
+			const float lo = floorf(tlo) - 1.f, hi = ceilf(thi) + 2.f;
+			if (lo > (float) za) za = (lo < 2e9f) ? (int) lo : 0x7fffffff;
+			if (hi < (float) zb) zb = (hi > -2e9f) ? (int) hi : 0;
+		}
+	}
+	za = __reduce_min_sync(0xffffffffu, za);
+	zb = __reduce_max_sync(0xffffffffu, zb);
+
+	if (za < zb) {
+		// replay the reference's additions up to the first visited slice
+#pragma unroll 8
+		for (int z = 0; z < za; ++z) { pos = pos + delta; cameraX = cameraX + cameraDelta; }
 		const size_t plane = (size_t) p.sx * p.sy;
-		short2* col = p.vol + (size_t) x + (size_t) y * p.sx + (size_t) (zs - p.z_begin) * plane;
-		const float dwm1 = (float) (p.dw - 1), dhm1 = (float) (p.dh - 1);
-		for (uint32_t z = zs; z < ze; ++z, pos = pos + delta, cameraX = cameraX + cameraDelta, col += plane) {
-			if (pos.z < 0.0001f) continue;
-			const float pxf = cameraX.x / cameraX.z + 0.5f, pyf = cameraX.y / cameraX.z + 0.5f;
-			if (pxf < 0 || pxf > dwm1 || pyf < 0 || pyf > dhm1) continue;
-			const uint32_t px = (uint32_t) pxf, py = (uint32_t) pyf;
-			const float d = __ldg(p.depth + px + (size_t) py * p.dw);
-			if (d == 0) continue;
-			const float diff = (d - cameraX.z) * sqrtf(1 + ksq(pos.x / pos.z) + ksq(pos.y / pos.z));
-			if (diff > -p.mu) {
-				const float sdf = kminf(1.f, diff / p.mu);
-				const short2 v = *col;
-				float tsdf = (float) v.x * 0.00003051944088f, wgt = (float) v.y;   // commons.h:160-163
-				tsdf = kclampf((wgt * tsdf + sdf) / (wgt + 1), -1.f, 1.f);
-				wgt = kminf(wgt + 1, p.maxweight);
-				*col = make_short2((short) (int) (tsdf * 32766.0f), (short) (int) wgt); // commons.h:182-185 (truncation)
-				++updated;
+		short2* col = p.vol + (size_t) x + (size_t) y * p.sx + (size_t) ((uint32_t) za - p.z_begin) * plane;
+		const bool fast = p.cull && p.mu > 0.f && p.dw <= 2048 && p.dh <= 2048;
+		const float mu = p.mu;
+		// INT_U consecutive slices per batch: all decisions first (depth gathers hit L1/L2), then all
+		// voxel loads back to back (INT_U independent 128-byte requests in flight per warp: the
+		// read-modify-write is latency-bound otherwise), then the updates and stores.
+		for (int z = za; z < zb; z += INT_U, col += INT_U * plane) {
+			float sdf[INT_U];
+			short2 v[INT_U];
+#pragma unroll
+			for (int u = 0; u < INT_U; ++u) {
+				sdf[u] = -4.f;   // "no update" (a real sdf is > -1)
+				const float3 P = pos, C = cameraX;
+				pos = pos + delta; cameraX = cameraX + cameraDelta;
+				if (!valid || z + u >= zb) continue;
+				if (P.z < 0.0001f) continue;
+				float pxf, pyf;
+				if (fast) {
+					pxf = __fdividef(C.x, C.z) + 0.5f;
+					pyf = __fdividef(C.y, C.z) + 0.5f;
+					// |approximate - exact| < 1e-3 for |q| < 2048: the truncated pixel and the bounds tests (integers
+					// 0, w-1, h-1) can only differ when the value is that close to an integer
+					if (fabsf(pxf - rintf(pxf)) < 1e-3f || fabsf(pyf - rintf(pyf)) < 1e-3f || !(fabsf(pxf) < 2048.f) || !(fabsf(pyf) < 2048.f)) {
+						pxf = C.x / C.z + 0.5f;
+						pyf = C.y / C.z + 0.5f;
+					}
+				} else {
+					pxf = C.x / C.z + 0.5f;
+					pyf = C.y / C.z + 0.5f;
+				}
+				if (pxf < 0 || pxf > dwm1 || pyf < 0 || pyf > dhm1) continue;
+				const uint32_t px = (uint32_t) pxf, py = (uint32_t) pyf;
+				const float d = __ldg(p.depth + px + (size_t) py * p.dw);
+				if (d == 0) continue;
+				const float e = d - C.z;
+				if (fast && e > mu) sdf[u] = 1.f;
+				else if (fast && e < -mu) continue;
+				else {
+					const float diff = e * sqrtf(1 + ksq(P.x / P.z) + ksq(P.y / P.z));
+					if (!(diff > -mu)) continue;
+					sdf[u] = kminf(1.f, diff / mu);
+				}
 			}
+#pragma unroll
+			for (int u = 0; u < INT_U; ++u)
+				if (sdf[u] > -2.f) v[u] = __ldcs(col + u * plane);
+#pragma unroll
+			for (int u = 0; u < INT_U; ++u)
+				if (sdf[u] > -2.f) {
+					float tsdf = (float) v[u].x * 0.00003051944088f, wgt = (float) v[u].y;   // commons.h:160-163
+					tsdf = kclampf((wgt * tsdf + sdf[u]) / (wgt + 1), -1.f, 1.f);
+					wgt = kminf(wgt + 1, p.maxweight);
+					__stcs(col + u * plane, make_short2((short) (int) (tsdf * 32766.0f), (short) (int) wgt)); // commons.h:182-185 (truncation)
+					++updated;
+				}
 		}
 	}
 	// exact N_upd: one atomic per warp
-	for (int o = 16; o > 0; o >>= 1) updated += __shfl_xor_sync(0xffffffffu, updated, o);
-	if (((threadIdx.y * blockDim.x + threadIdx.x) & 31) == 0 && updated) atomicAdd(p.n_upd, (unsigned long long) updated);
+	updated = __reduce_add_sync(0xffffffffu, updated);
+	if ((threadIdx.x & 31) == 0 && updated) atomicAdd(p.n_upd, (unsigned long long) updated);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -20,6 +20,7 @@ KFB_MAX_LEVELS = 8
 FLAG_ICP_HOST_SOLVE = 0x1
 FLAG_TRACK_STATUS = 0x2
 FLAG_NO_GRAPHS = 0x4
+FLAG_INTEGRATE_NO_CULL = 0x8
 
 (BUF_VOLUME, BUF_VERTEX, BUF_NORMAL, BUF_FLOATDEPTH, BUF_SCALEDDEPTH, BUF_INVERTEX, BUF_INNORMAL,
  BUF_REDUCTION, BUF_TRACKSTATUS, BUF_RAYCASTPOSE, BUF_OLDPOSE, BUF_GAUSSIAN, BUF_INPUTDEPTH) = range(13)

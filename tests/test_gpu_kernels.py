@@ -315,3 +315,61 @@ def test_render_kernels(port, gpu, state):
     gpu.trackReduceKernel(0, state["pose5"], pr)
     assert np.array_equal(gpu.read(kf.BUF_TRACKSTATUS), td["result"].astype(np.int8))
     assert np.array_equal(gpu.renderTrack(), port.render_track(td))
+
+
+def _random_pose(rng, scale=1.0):
+    from slambench_b200 import synth
+
+    pose = np.eye(4, dtype=np.float32)
+    pose[:3, :3] = synth.rpy_to_R(*(rng.uniform(-1, 1, 3) * scale)).astype(np.float32)
+    pose[:3, 3] = rng.uniform(-0.5, 5.3, 3)   # sometimes outside the volume cube
+    return pose
+
+
+@pytest.mark.parametrize("vres", [96, 256])
+def test_integrate_culling_is_exact(port, seq16, vres):
+    """The conservative z-interval + approximate-division fast paths must not change one voxel:
+    compare with the same kernel visiting every voxel with the reference's full expression
+    (KFB_FLAG_INTEGRATE_NO_CULL), over random poses (camera inside/outside the cube, large rotations),
+    holey depth maps and accumulated weights; at 96^3 also against the oracle."""
+    depth, _ = seq16
+    rng = np.random.default_rng(vres)
+    d = depth[7].copy()
+    d[rng.random(d.shape) < 0.05] = 0
+    d[200:260, 300:420] = 700
+    with kf.Kfusion((640, 480), vres, 4.8, T0, (10, 5, 4)) as a, \
+            kf.Kfusion((640, 480), vres, 4.8, T0, (10, 5, 4), flags=kf.FLAG_INTEGRATE_NO_CULL) as b:
+        a.preprocessing(d)      # also produces max(depth) for the far cull
+        b.preprocessing(d)
+        want = port.init_volume((vres,) * 3) if vres <= 96 else None
+        raw = port.mm2meters(d, (640, 480))
+        poses = [kf.identity_pose(T0)] + [_random_pose(rng, s) for s in (0.05, 0.05, 0.3, 0.3, 1.0, 1.0, 3.0)]
+        total = 0
+        for i, pose in enumerate(poses):
+            mu = (0.1, 0.05, 0.3)[i % 3]
+            a.reset_stats(); b.reset_stats()
+            a.integrateKernel(a.inverse(pose), a.cameraMatrix(K), mu)
+            b.integrateKernel(b.inverse(pose), b.cameraMatrix(K), mu)
+            na, nb = a.stats()["voxels_updated_last"], b.stats()["voxels_updated_last"]
+            assert na == nb, f"pose {i}: N_upd {na} != {nb}"
+            total += na
+            va, vb = a.read(kf.BUF_VOLUME), b.read(kf.BUF_VOLUME)
+            assert np.array_equal(va, vb), f"pose {i}: {int((va != vb).any(-1).sum())} voxels differ"
+            if want is not None:
+                port.integrate(want, DIM, raw, port.inverse(pose), port.camera_matrix(K), mu)
+                assert np.array_equal(va, want), f"pose {i} vs oracle"
+        assert total > 0.05 * vres ** 3
+
+
+def test_integrate_culling_exact_with_teacher_forced_depth(port, gpu, state):
+    """Depth written from the host (no cached max(depth) => no far cull) and a non-cubic volume."""
+    rng = np.random.default_rng(9)
+    res, dim = (80, 48, 112), np.array([4.8, 2.9, 4.8], np.float32)
+    with kf.Kfusion((640, 480), res, dim, T0, (10, 5, 4)) as g:
+        want = port.init_volume(res)
+        g.write(kf.BUF_FLOATDEPTH, state["floatDepth6"])
+        for s in (0.0, 0.1, 0.6):
+            pose = kf.identity_pose(T0) if s == 0 else _random_pose(rng, s)
+            port.integrate(want, dim, state["floatDepth6"], port.inverse(pose), port.camera_matrix(K), MU)
+            g.integrateKernel(g.inverse(pose), g.cameraMatrix(K), MU)
+            assert np.array_equal(g.read(kf.BUF_VOLUME), want)

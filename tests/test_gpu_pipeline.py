@@ -168,3 +168,34 @@ def test_full_size_512_integrate_properties(port, seq16):
         assert st["voxels_updated_last"] == n1 and st["voxels_updated_total"] == 2 * n1
         got2 = g.read(kf.BUF_VOLUME)
         assert int((got2[..., 1] == 2).sum()) == n1 and int((got2[..., 1] == 1).sum()) == 0
+
+
+def test_device_resident_icp_matches_host_loop(seq16):
+    """Default: the whole ICP schedule runs on the device (solve + SE3 exp + per-level break in the last CTA,
+    certified-Cholesky fast path).  KFB_FLAG_ICP_HOST_SOLVE: one launch + host Jacobi solve per iteration,
+    the reference's control flow verbatim.  Same poses (<= 2e-6), same flags, same iteration counts."""
+    depth, _ = seq16
+    n = 14
+    its = {}
+
+    def count(tag):
+        def f(fr, g):
+            its.setdefault(tag, []).append(g.stats()["icp_iterations_last"])
+        return f
+
+    p_dev, t_dev, i_dev = run_gpu_pipeline(depth, n, 128, on_frame=count("dev"))
+    p_host, t_host, i_host = run_gpu_pipeline(depth, n, 128, flags=kf.FLAG_ICP_HOST_SOLVE, on_frame=count("host"))
+    assert t_dev == t_host and i_dev == i_host
+    assert np.abs(p_dev - p_host).max() <= 2e-6
+    assert its["dev"] == its["host"], (its["dev"], its["host"])
+    assert its["dev"][:4] == [3, 3, 3, 3] and max(its["dev"]) <= 19
+
+
+def test_zero_iteration_pyramid_levels(port, seq16):
+    """-y 0,0,4 style schedules: levels with zero iterations are skipped (cpp/kernels.cpp:952)."""
+    depth, _ = seq16
+    pyr = (3, 0, 2)
+    p_cpu, t_cpu, i_cpu = run_cpu_pipeline(port, depth, 8, 64, pyramid=pyr)
+    p_gpu, t_gpu, i_gpu = run_gpu_pipeline(depth, 8, 64, pyramid=pyr)
+    assert t_gpu == t_cpu and i_gpu == i_cpu
+    assert np.abs(p_gpu - p_cpu).max() <= 1e-4
