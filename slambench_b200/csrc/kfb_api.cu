@@ -80,8 +80,9 @@ struct kfb_ctx {
 	unsigned int* d_counter;
 	float* d_out32;
 	float* h_out32;             // mapped pinned: [0..31] result, [32] seq flag, [48..63] pose, [64] iterations
-	IcpState* d_icp;            // device-resident ICP loop state
-	IcpState* h_icp_stage;      // pinned staging for the per-frame initial state
+	unsigned int* d_bar;        // k_icp grid barrier: [0] arrivals, [1] generation, [2] converged
+	float* d_pose;              // k_icp: current pose [16]
+	int icp_grid;               // co-resident CTAs for the cooperative launch
 	float* h_out32_dev;
 	uint32_t seq;
 	unsigned long long* d_nupd; // NUPD_SLOTS per-integrate counters
@@ -238,9 +239,19 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	CK(cudaMemsetAsync(c->d_out32, 0, 32 * sizeof(float), c->stream));
 	CK(cudaHostAlloc(&c->h_out32, 128 * sizeof(float), cudaHostAllocMapped));
 	memset(c->h_out32, 0, 128 * sizeof(float));
-	CK(cudaMalloc(&c->d_icp, sizeof(IcpState)));
-	CK(cudaMemsetAsync(c->d_icp, 0, sizeof(IcpState), c->stream));
-	CK(cudaHostAlloc(&c->h_icp_stage, sizeof(IcpState), cudaHostAllocDefault));
+	CK(cudaMalloc(&c->d_bar, 4 * sizeof(unsigned int)));
+	CK(cudaMemsetAsync(c->d_bar, 0, 4 * sizeof(unsigned int), c->stream));
+	CK(cudaMalloc(&c->d_pose, 16 * sizeof(float)));
+	{
+		int coop = 0, per_sm = 0, sms = 0;
+		CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+		CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp, TR_THREADS, 0));
+		if (!coop || per_sm < 1) return set_err(KFB_E_CUDA, "device cannot co-schedule the ICP kernel (cooperative launch %d, CTAs/SM %d)", coop, per_sm);
+		if (per_sm > 2) per_sm = 2;
+		c->icp_grid = sms * per_sm;
+		if (c->icp_grid > TR_MAX_BLOCKS) c->icp_grid = TR_MAX_BLOCKS;
+	}
 	CK(cudaHostGetDevicePointer(&c->h_out32_dev, c->h_out32, 0));
 	CK(cudaMalloc(&c->d_nupd, NUPD_SLOTS * sizeof(unsigned long long)));
 	CK(cudaMalloc(&c->d_dmax, 2 * sizeof(unsigned int)));
@@ -270,7 +281,7 @@ int kfb_destroy(kfb_ctx* c) {
 	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_floatDepth);
 	for (int l = 0; l < c->levels; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
 	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax);
-	cudaFreeHost(c->h_out32); cudaFree(c->d_icp); cudaFreeHost(c->h_icp_stage);
+	cudaFreeHost(c->h_out32); cudaFree(c->d_bar); cudaFree(c->d_pose);
 	if (c->d_input) cudaFree(c->d_input);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->d_render) cudaFree(c->d_render);
@@ -424,9 +435,7 @@ static int wait_seq(kfb_ctx* c, uint32_t seq) {
 	return 0;
 }
 
-// icp_mode: 0 = host loop (result published every launch), 1 = device-resident loop, 2 = same and last launch of the frame
-static int launch_track(kfb_ctx* c, int level, const float* T, const float* V, float dist, float nthr, bool wait, int icp_mode = 0,
-		float icp_threshold = 0.f) {
+static int launch_track(kfb_ctx* c, int level, const float* T, const float* V, float dist, float nthr, bool wait) {
 	TrackParams p;
 	memset(&p, 0, sizeof p);
 	p.inV = c->d_inV[level]; p.inN = c->d_inN[level];
@@ -439,13 +448,8 @@ static int launch_track(kfb_ctx* c, int level, const float* T, const float* V, f
 	p.partials = c->d_partials; p.counter = c->d_counter; p.out32 = c->d_out32;
 	p.out32_host = c->h_out32_dev;
 	p.seq_host = (volatile uint32_t*) (c->h_out32_dev + 32);
-	p.seq = (icp_mode == 1) ? c->seq : ++c->seq;
+	p.seq = ++c->seq;
 	p.status = (c->cfg.flags & KFB_FLAG_TRACK_STATUS) ? c->d_status : nullptr;
-	p.icp = nullptr; p.level = level; p.is_final = 0; p.icp_threshold = icp_threshold; p.pose_host = c->h_out32_dev + 48;
-	if (icp_mode) {
-		p.icp = c->d_icp; p.is_final = (icp_mode == 2);
-		p.pose_dev = c->d_icp->pose; p.view_dev = c->d_icp->view;
-	}
 	const uint32_t blocks = track_blocks(p.w * (p.row1 - p.row0));
 	k_track_reduce<<<blocks, TR_THREADS, 0, c->stream>>>(p);
 	LAUNCHED(c);
@@ -498,27 +502,36 @@ int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracki
 			}
 		}
 	} else {
-		// device-resident loop: the whole schedule is enqueued; solve, pose update and the per-level
-		// `break` happen in the last CTA of each launch; ONE host wait per frame
-		int total = 0, last_level = -1;
-		for (int level = 0; level < c->levels; ++level) if (c->cfg.iterations[level] > 0) { total += c->cfg.iterations[level]; if (last_level < 0) last_level = level; }
+		// device-resident loop: ONE persistent cooperative kernel runs the whole schedule (solve, pose
+		// update and the per-level `break` in its last-arriving CTA); ONE host wait per frame
+		int total = 0;
+		for (int level = 0; level < c->levels; ++level) total += c->cfg.iterations[level] > 0 ? c->cfg.iterations[level] : 0;
 		if (total > 0) {
-			IcpState* st = c->h_icp_stage;
-			memcpy(st->pose, c->pose, sizeof st->pose);
-			memcpy(st->view, projectReference, sizeof st->view);
-			memset(st->done, 0, sizeof st->done);
-			st->iters = 0;
-			CK(cudaMemcpyAsync(c->d_icp, st, sizeof(IcpState), cudaMemcpyHostToDevice, c->stream));
-			c->st.h2d_bytes += sizeof(IcpState);
-			++c->seq;
-			for (int level = c->levels - 1; level >= 0; --level)
-				for (int i = 0; i < c->cfg.iterations[level]; ++i) {
-					const bool fin = (level == last_level) && (i == c->cfg.iterations[level] - 1);
-					rc = launch_track(c, level, c->pose, projectReference, c_dist_threshold, c_normal_threshold, false, fin ? 2 : 1, icp_threshold);
-					if (rc) return rc;
-				}
-			rc = wait_seq(c, c->seq);
+			IcpParams p;
+			memset(&p, 0, sizeof p);
+			for (int l = 0; l < c->levels; ++l) {
+				p.inV[l] = c->d_inV[l]; p.inN[l] = c->d_inN[l]; p.w[l] = c->lw[l]; p.h[l] = c->lh[l];
+				p.iterations[l] = c->cfg.iterations[l];
+			}
+			p.levels = c->levels;
+			p.refV = c->d_vertex; p.refN = c->d_normal; p.rw = c->cw; p.rh = c->ch;
+			p.pose0 = toMat(c->pose); p.view = toMat(projectReference);
+			p.dist_threshold = c_dist_threshold; p.normal_threshold = c_normal_threshold; p.icp_threshold = icp_threshold;
+			p.partials = c->d_partials; p.bar = c->d_bar; p.pose_dev = c->d_pose;
+			p.out_host = c->h_out32_dev;
+			p.seq = ++c->seq;
+			p.status = (c->cfg.flags & KFB_FLAG_TRACK_STATUS) ? c->d_status : nullptr;
+			c->h_out32[33] = 0.f;
+			void* args[] = { &p };
+			CK(cudaLaunchCooperativeKernel((const void*) k_icp, dim3(c->icp_grid), dim3(TR_THREADS), args, 0, c->stream));
+			LAUNCHED(c);
+			rc = wait_seq(c, p.seq);
 			if (rc) return rc;
+			if (*(volatile uint32_t*) (c->h_out32 + 33) != 0) {
+				cudaStreamSynchronize(c->stream);
+				cudaMemsetAsync(c->d_bar, 0, 4 * sizeof(unsigned int), c->stream);
+				return set_err(KFB_E_CUDA, "ICP kernel: grid barrier timed out");
+			}
 			memcpy(c->reduction, c->h_out32, 32 * sizeof(float));
 			memcpy(c->pose, c->h_out32 + 48, 16 * sizeof(float));
 			iters = *(volatile uint32_t*) (c->h_out32 + 64);

@@ -167,15 +167,6 @@ __global__ void __launch_bounds__(256) k_pyramid(PyrParams p) {
 #define TR_THREADS 256
 #define TR_MAX_BLOCKS 1184  // 148 SMs x 8
 
-// device-resident ICP loop state (one per context): the whole level/iteration schedule of
-// Kfusion::tracking (cpp/kernels.cpp:950-967) is enqueued up front; each launch first looks here.
-struct IcpState {
-	float pose[16];          // current estimate, updated by the last CTA of every active iteration (:963)
-	float view[16];          // projectReference (:948), constant during a frame
-	int done[8];             // level converged: updatePoseKernel returned true => `break` (:963-964)
-	unsigned int iters;      // active iterations so far
-};
-
 struct TrackParams {
 	const float* inV; const float* inN;     // packed float3[w*h] of this level
 	const float* refV; const float* refN;   // packed float3[rw*rh] (raycast maps, world frame)
@@ -190,25 +181,7 @@ struct TrackParams {
 	float* out32;                           // device result
 	float* out32_host; volatile uint32_t* seq_host; uint32_t seq;  // optional mapped-host mirror + sequence flag
 	int8_t* status;                         // optional per-pixel result plane (stride rw), for renderTrack
-	IcpState* icp;                          // device-resident loop (nullptr: one launch per host iteration)
-	int level, is_final;
-	float icp_threshold;
-	float* pose_host;                       // mapped-host mirror of icp->pose [16] followed by iters [1]
 };
-
-// 6x6 solve + SE3 exp + pose composition by ONE thread of the last CTA (updatePoseKernel, :759-775)
-__device__ __noinline__ void icp_update_pose(const TrackParams& p, const float* red32) {
-	float pose[16];
-#pragma unroll
-	for (int i = 0; i < 16; ++i) pose[i] = p.icp->pose[i];
-	const int conv = hm_update_pose_fast(pose, red32, p.icp_threshold);
-#pragma unroll
-	for (int i = 0; i < 16; ++i) { p.icp->pose[i] = pose[i]; p.pose_host[i] = pose[i]; }
-	if (conv) p.icp->done[p.level] = 1;
-	const unsigned int it = p.icp->iters + 1;
-	p.icp->iters = it;
-	reinterpret_cast<volatile unsigned int*>(p.pose_host)[16] = it;
-}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -217,83 +190,92 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 
+// per-thread accumulators of the 32 reduction outputs (reduceKernel, cpp/kernels.cpp:251-495)
+struct TrackAcc {
+	float s[28];
+	int c28, c29, c30, c31;
+	__device__ __forceinline__ void clear() {
+#pragma unroll
+		for (int i = 0; i < 28; ++i) s[i] = 0.f;
+		c28 = c29 = c30 = c31 = 0;
+	}
+};
+
+// trackKernel for ONE input pixel (cpp/kernels.cpp:497-560) folded straight into the sums
+__device__ __forceinline__ void track_pixel(TrackAcc& a, const float* __restrict__ inV, const float* __restrict__ inN,
+		const float* __restrict__ refV, const float* __restrict__ refN, uint32_t w, uint32_t rw, uint32_t rh, uint32_t px, uint32_t py,
+		const Mat4& T, const Mat4& V, float dist_threshold, float normal_threshold, int8_t* status) {
+	const size_t idx = (size_t) px + (size_t) py * w;
+	int result;
+	float err = 0.f;
+	float3 Ja = f3(0, 0, 0), Jb = f3(0, 0, 0);
+	const float3 n = ld3(inN, idx);
+	if (n.x == KFB_INVALID) {
+		result = -1;
+	} else {
+		const float3 pv = mat_point(T, ld3(inV, idx));
+		const float3 pp = mat_point(V, pv);
+		const float pixx = pp.x / pp.z + 0.5f, pixy = pp.y / pp.z + 0.5f;
+		if (pixx < 0 || pixx > (float) (rw - 1) || pixy < 0 || pixy > (float) (rh - 1)) {
+			result = -2;
+		} else {
+			// (uint)NaN is 0 on x86-64 (cvttss2si, low 32 bits) and here (cvt.rzi) — start-up frames
+			const uint32_t rx = (uint32_t) pixx, ry = (uint32_t) pixy;
+			const size_t ridx = (size_t) rx + (size_t) ry * rw;
+			const float3 rn = ld3(refN, ridx);
+			if (rn.x == KFB_INVALID) {
+				result = -3;
+			} else {
+				const float3 diff = ld3(refV, ridx) - pv;
+				const float3 pn = mat_rotate(T, n);
+				if (klength(diff) > dist_threshold) result = -4;
+				else if (kdot(pn, rn) < normal_threshold) result = -5;
+				else {
+					result = 1;
+					err = kdot(rn, diff);
+					Ja = rn;
+					Jb = kcross(pv, rn);
+				}
+			}
+		}
+	}
+	if (status) status[(size_t) px + (size_t) py * rw] = (int8_t) result;
+	if (result < 1) {
+		a.c29 += (result == -4);
+		a.c30 += (result == -5);
+		a.c31 += (result > -4);
+	} else {
+		const float J[6] = { Ja.x, Ja.y, Ja.z, Jb.x, Jb.y, Jb.z };
+		a.s[0] += err * err;
+#pragma unroll
+		for (int k = 0; k < 6; ++k) a.s[1 + k] += err * J[k];
+		int q = 7;
+#pragma unroll
+		for (int i = 0; i < 6; ++i)
+#pragma unroll
+			for (int j = i; j < 6; ++j) a.s[q++] += J[i] * J[j];
+		a.c28 += 1;
+	}
+}
+
 __global__ void __launch_bounds__(TR_THREADS) k_track_reduce(TrackParams p) {
 	__shared__ double sm[TR_THREADS / 32][32];
-	__shared__ float red32[32];
 	__shared__ bool is_last;
 	Mat4 T, V;
-	if (p.icp && p.icp->done[p.level]) {
-		// this level already converged: the reference's `break`.  The last launch of the frame still
-		// publishes the sequence number the host is waiting for (results were published by the last
-		// active iteration, a kernel boundary ago).
-		if (p.is_final && blockIdx.x == 0 && threadIdx.x == 0 && p.seq_host) *p.seq_host = p.seq;
-		return;
-	}
 	if (p.pose_dev) {
 #pragma unroll
 		for (int i = 0; i < 16; ++i) { T.m[i] = p.pose_dev[i]; V.m[i] = p.view_dev[i]; }
 	} else { T = p.Ttrack; V = p.view; }
 
-	float s[28];
-#pragma unroll
-	for (int i = 0; i < 28; ++i) s[i] = 0.f;
-	int c28 = 0, c29 = 0, c30 = 0, c31 = 0;
-
+	TrackAcc acc;
+	acc.clear();
 	const uint32_t npx = (p.row1 - p.row0) * p.w;
 	for (uint32_t i = blockIdx.x * TR_THREADS + threadIdx.x; i < npx; i += gridDim.x * TR_THREADS) {
 		const uint32_t py = p.row0 + i / p.w, px = i % p.w;
-		const size_t idx = (size_t) px + (size_t) py * p.w;
-		int result;
-		float err = 0.f;
-		float3 Ja = f3(0, 0, 0), Jb = f3(0, 0, 0);
-		const float3 n = ld3(p.inN, idx);
-		if (n.x == KFB_INVALID) {
-			result = -1;
-		} else {
-			const float3 pv = mat_point(T, ld3(p.inV, idx));
-			const float3 pp = mat_point(V, pv);
-			const float pixx = pp.x / pp.z + 0.5f, pixy = pp.y / pp.z + 0.5f;
-			if (pixx < 0 || pixx > (float) (p.rw - 1) || pixy < 0 || pixy > (float) (p.rh - 1)) {
-				result = -2;
-			} else {
-				// (uint)NaN is 0 on x86-64 (cvttss2si, low 32 bits) and here (cvt.rzi) — start-up frames
-				const uint32_t rx = (uint32_t) pixx, ry = (uint32_t) pixy;
-				const size_t ridx = (size_t) rx + (size_t) ry * p.rw;
-				const float3 rn = ld3(p.refN, ridx);
-				if (rn.x == KFB_INVALID) {
-					result = -3;
-				} else {
-					const float3 diff = ld3(p.refV, ridx) - pv;
-					const float3 pn = mat_rotate(T, n);
-					if (klength(diff) > p.dist_threshold) result = -4;
-					else if (kdot(pn, rn) < p.normal_threshold) result = -5;
-					else {
-						result = 1;
-						err = kdot(rn, diff);
-						Ja = rn;
-						Jb = kcross(pv, rn);
-					}
-				}
-			}
-		}
-		if (p.status) p.status[(size_t) px + (size_t) py * p.rw] = (int8_t) result;
-		if (result < 1) {
-			c29 += (result == -4);
-			c30 += (result == -5);
-			c31 += (result > -4);
-		} else {
-			const float J[6] = { Ja.x, Ja.y, Ja.z, Jb.x, Jb.y, Jb.z };
-			s[0] += err * err;
-#pragma unroll
-			for (int k = 0; k < 6; ++k) s[1 + k] += err * J[k];
-			int q = 7;
-#pragma unroll
-			for (int a = 0; a < 6; ++a)
-#pragma unroll
-				for (int b = a; b < 6; ++b) s[q++] += J[a] * J[b];
-			c28 += 1;
-		}
+		track_pixel(acc, p.inV, p.inN, p.refV, p.refN, p.w, p.rw, p.rh, px, py, T, V, p.dist_threshold, p.normal_threshold, p.status);
 	}
+	float* s = acc.s;
+	const int c28 = acc.c28, c29 = acc.c29, c30 = acc.c30, c31 = acc.c31;
 
 	// warp -> CTA -> grid, all in fp64 and in a fixed order
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -337,16 +319,154 @@ __global__ void __launch_bounds__(TR_THREADS) k_track_reduce(TrackParams p) {
 		p.out32[lane] = r;
 		if (p.out32_host) p.out32_host[lane] = r;
 		if (lane == 0) *p.counter = 0;  // re-arm for the next launch
-		if (p.icp) {
-			red32[lane] = r;
-			__syncwarp();
-			if (lane == 0) icp_update_pose(p, red32);
-		}
 		__syncwarp();
-		if (p.seq_host && (!p.icp || p.is_final)) {
+		if (p.seq_host) {
 			__threadfence_system();
 			if (lane == 0) *p.seq_host = p.seq;
 		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
+// The WHOLE ICP loop of Kfusion::tracking (cpp/kernels.cpp:950-967) as ONE persistent
+// cooperative kernel: for level = L-1..0, for i < iterations[level]: fused track+reduce over this
+// level's pixels -> per-CTA fp64 partials -> grid barrier; the LAST CTA to arrive sums the partials
+// in a fixed order, solves the 6x6 system (updatePoseKernel, :759-775: certified Cholesky fast
+// path, Jacobi pseudo-inverse fallback), composes the new pose, decides the per-level `break`,
+// mirrors pose + sums to mapped host memory and releases the barrier.  No launch, no host round
+// trip and no skipped work between iterations; the host waits once per frame.
+// Launched with cudaLaunchCooperativeKernel (all CTAs co-resident: they wait on one another).
+// ------------------------------------------------------------------------------------------
+#define ICP_MAX_LEVELS 3
+struct IcpParams {
+	const float* inV[ICP_MAX_LEVELS]; const float* inN[ICP_MAX_LEVELS];
+	uint32_t w[ICP_MAX_LEVELS], h[ICP_MAX_LEVELS];
+	int iterations[ICP_MAX_LEVELS];
+	int levels;
+	const float* refV; const float* refN;
+	uint32_t rw, rh;
+	Mat4 pose0, view;                       // pose at entry (:947), projectReference (:948)
+	float dist_threshold, normal_threshold, icp_threshold;
+	double* partials;                       // [gridDim.x][32]
+	unsigned int* bar;                      // [0] arrival counter, [1] generation, [2] converged flag of the last solve
+	float* pose_dev;                        // [16] current pose (global; rewritten by the last CTA each iteration)
+	float* out_host;                        // mapped: [0..31] sums, [32] seq, [33] error, [48..63] pose, [64] iterations
+	uint32_t seq;
+	int8_t* status;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+	unsigned int v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) {
+	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// one thread: updatePoseKernel (:759-775)
+__device__ __noinline__ int icp_solve(float* pose_dev, float* out_host, const float* red32, float icp_threshold) {
+	float pose[16];
+#pragma unroll
+	for (int i = 0; i < 16; ++i) pose[i] = pose_dev[i];
+	const int conv = hm_update_pose_fast(pose, red32, icp_threshold);
+#pragma unroll
+	for (int i = 0; i < 16; ++i) { pose_dev[i] = pose[i]; out_host[48 + i] = pose[i]; }
+	return conv;
+}
+
+__global__ void __launch_bounds__(TR_THREADS, 2) k_icp(IcpParams p) {
+	__shared__ double sm[TR_THREADS / 32][32];
+	__shared__ float red32[32];
+	__shared__ Mat4 Tsh;
+	__shared__ int flag_sh;   // bit 0: this CTA arrived last; after the barrier: converged / error
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const unsigned int gen0 = ld_acquire_u32(p.bar + 1);   // nobody advances it before every CTA has arrived once
+	unsigned int step = 0, iters = 0;
+	const Mat4 V = p.view;
+
+	for (int level = p.levels - 1; level >= 0; --level) {
+		const uint32_t w = p.w[level], npx = p.w[level] * p.h[level];
+		for (int it = 0; it < p.iterations[level]; ++it) {
+			if (threadIdx.x < 16) Tsh.m[threadIdx.x] = (step == 0) ? p.pose0.m[threadIdx.x] : __ldcg(p.pose_dev + threadIdx.x);
+			__syncthreads();
+			const Mat4 T = Tsh;
+			TrackAcc acc;
+			acc.clear();
+			for (uint32_t i = blockIdx.x * TR_THREADS + threadIdx.x; i < npx; i += gridDim.x * TR_THREADS)
+				track_pixel(acc, p.inV[level], p.inN[level], p.refV, p.refN, w, p.rw, p.rh, i % w, i / w, T, V, p.dist_threshold,
+						p.normal_threshold, p.status);
+			// warp -> CTA, fp64, fixed order
+#pragma unroll
+			for (int i = 0; i < 28; ++i) {
+				const double v = warp_sum((double) acc.s[i]);
+				if (lane == 0) sm[wid][i] = v;
+			}
+			{
+				const double v28 = warp_sum((double) acc.c28), v29 = warp_sum((double) acc.c29), v30 = warp_sum((double) acc.c30),
+						v31 = warp_sum((double) acc.c31);
+				if (lane == 0) { sm[wid][28] = v28; sm[wid][29] = v29; sm[wid][30] = v30; sm[wid][31] = v31; }
+			}
+			__syncthreads();
+			if (wid == 0) {
+				double v = 0;
+#pragma unroll
+				for (int k = 0; k < TR_THREADS / 32; ++k) v += sm[k][lane];
+				__stcg(p.partials + (size_t) blockIdx.x * 32 + lane, v);
+				__threadfence();
+			}
+			__syncthreads();
+			++step; ++iters;
+			if (threadIdx.x == 0) flag_sh = (atomicAdd(p.bar, 1u) == gridDim.x - 1) ? 1 : 0;
+			__syncthreads();
+			if (flag_sh) {
+				// last CTA: every partial row is visible (each writer fenced before its ticket)
+				__threadfence();
+				double v = 0;
+				for (uint32_t b = wid; b < gridDim.x; b += TR_THREADS / 32) v += __ldcg(p.partials + (size_t) b * 32 + lane);
+				__syncthreads();
+				sm[wid][lane] = v;
+				__syncthreads();
+				if (wid == 0) {
+					double t = 0;
+#pragma unroll
+					for (int k = 0; k < TR_THREADS / 32; ++k) t += sm[k][lane];
+					const float r = (float) t;
+					red32[lane] = r;
+					p.out_host[lane] = r;
+					__syncwarp();
+					if (lane == 0) {
+						if (step == 1) {
+#pragma unroll
+							for (int i = 0; i < 16; ++i) p.pose_dev[i] = p.pose0.m[i];
+						}
+						const int c = icp_solve(p.pose_dev, p.out_host, red32, p.icp_threshold);
+						reinterpret_cast<volatile unsigned int*>(p.out_host)[64] = iters;
+						p.bar[2] = (unsigned int) c;
+						p.bar[0] = 0;                       // re-arm the arrival counter
+						__threadfence_system();             // pose + sums reach the host before anybody can publish `seq`
+						st_release_u32(p.bar + 1, gen0 + step);
+					}
+				}
+			} else if (threadIdx.x == 0) {
+				unsigned long long spins = 0;
+				while (ld_acquire_u32(p.bar + 1) != gen0 + step) {
+					if (++spins > (1ull << 22)) { flag_sh = 2; break; }   // ~1 s: a lost CTA must not hang the GPU
+				}
+			}
+			__syncthreads();
+			if (flag_sh == 2) {   // barrier time-out (cannot happen under a cooperative launch): report and leave
+				if (threadIdx.x == 0) { reinterpret_cast<volatile unsigned int*>(p.out_host)[33] = 1u; __threadfence_system(); }
+				return;
+			}
+			const unsigned int converged = __ldcg(p.bar + 2);
+			__syncthreads();
+			if (converged) break;   // updatePoseKernel returned true: next level (:963-964)
+		}
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		__threadfence_system();
+		*reinterpret_cast<volatile unsigned int*>(p.out_host + 32) = p.seq;
 	}
 }
 
