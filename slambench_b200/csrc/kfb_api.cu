@@ -87,6 +87,11 @@ struct kfb_ctx {
 	uint32_t seq;
 	unsigned long long* d_nupd; // NUPD_SLOTS per-integrate counters
 	unsigned int* d_dmax;       // two slots: bit pattern of max(floatDepth), written by preprocess (ping-pong)
+	uint32_t int_zchunk;        // integrate piece length override (KFB_INT_ZCHUNK, tuning)
+	uint2* d_queue; size_t queue_cap;   // integrate work list
+	unsigned int* d_queue_ctr;  // 2 slots x {count, head}
+	int int_grid;               // persistent CTAs of k_integrate_run
+	uint64_t int_launches;
 	int dmax_slot;              // slot holding the max of the CURRENT floatDepth, -1 = unknown
 	uint64_t preprocess_count;
 	uint64_t integrate_count;
@@ -257,6 +262,19 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	CK(cudaMalloc(&c->d_dmax, 2 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_dmax, 0, 2 * sizeof(unsigned int), c->stream));
 	c->dmax_slot = -1; c->preprocess_count = 0;
+	{ const char* e = getenv("KFB_INT_ZCHUNK"); c->int_zchunk = e ? (uint32_t) atoi(e) : 0; }
+	c->d_queue = nullptr; c->queue_cap = 0; c->int_launches = 0;
+	CK(cudaMalloc(&c->d_queue_ctr, 4 * sizeof(unsigned int)));
+	CK(cudaMemsetAsync(c->d_queue_ctr, 0, 4 * sizeof(unsigned int), c->stream));
+	{
+		int per_sm = 0, sms = 0;
+		CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_integrate_run, 256, 0));
+		if (per_sm < 1) per_sm = 1;
+		const char* e = getenv("KFB_INT_CTAS_PER_SM");
+		if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e);
+		c->int_grid = sms * per_sm;
+	}
 	// single-slab view by default
 	memset(&c->view_all, 0, sizeof c->view_all);
 	c->view_all.n_slabs = 1;
@@ -280,7 +298,7 @@ int kfb_destroy(kfb_ctx* c) {
 	for (int i = 0; i < KFB_MAX_SLABS; ++i) if (c->peer_ptrs[i]) cudaIpcCloseMemHandle(c->peer_ptrs[i]);
 	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_floatDepth);
 	for (int l = 0; l < c->levels; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
-	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax);
+	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax); cudaFree(c->d_queue_ctr); if (c->d_queue) cudaFree(c->d_queue);
 	cudaFreeHost(c->h_out32); cudaFree(c->d_bar); cudaFree(c->d_pose);
 	if (c->d_input) cudaFree(c->d_input);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -561,16 +579,31 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	const uint32_t slot = (uint32_t) (c->integrate_count % NUPD_SLOTS);
 	if (c->integrate_count >= NUPD_SLOTS) CK(cudaMemsetAsync(c->d_nupd + slot, 0, sizeof(unsigned long long), c->stream));
 	p.n_upd = c->d_nupd + slot;
-	// enough z-chunks to put >= ~600k threads in flight (148 SMs x 2048 threads x 2)
-	const uint32_t nz = c->z1 - c->z0;
-	const uint64_t cols = (uint64_t) p.sx * p.sy;
-	uint32_t chunks = (uint32_t) ((148ull * 2048ull * 2ull + cols - 1) / cols);
-	if (chunks < 1) chunks = 1;
-	if (chunks > nz) chunks = nz;
-	p.zchunk = (nz + chunks - 1) / chunks;
-	chunks = (nz + p.zchunk - 1) / p.zchunk;
-	dim3 block(32, 8), grid((p.sx + 31) / 32, (p.sy + 7) / 8, chunks);
-	k_integrate<<<grid, block, 0, c->stream>>>(p);
+	// pass 1 cuts every warp-column's visited interval into pieces of `zchunk` slices; pass 2 is persistent
+	// short pieces keep every warp's serial chain short (measured: 256^3 best at 16-32, 512^3 at 64)
+	{
+		uint32_t zc = (c->z1 - c->z0) / 8;
+		zc = zc < 16 ? 16 : (zc > 64 ? 64 : zc);
+		p.zchunk = c->int_zchunk ? c->int_zchunk : zc;
+	}
+	const int qslot = (int) (c->int_launches++ & 1);   // never reset: the slots alternate strictly
+	p.queue = c->d_queue;
+	p.queue_count = c->d_queue_ctr + 2 * qslot; p.queue_head = p.queue_count + 1;
+	p.queue_next = c->d_queue_ctr + 2 * (qslot ^ 1);
+	{
+		const uint32_t nz = c->z1 - c->z0;
+		const size_t need = (size_t) ((p.sx + 31) / 32) * p.sy * ((nz + p.zchunk - 1) / p.zchunk + 1);
+		if (need > c->queue_cap) {
+			if (c->d_queue) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(c->d_queue)); }
+			CK(cudaMalloc(&c->d_queue, need * sizeof(uint2)));
+			c->queue_cap = need;
+			p.queue = c->d_queue;
+		}
+	}
+	dim3 block(32, 8), grid((p.sx + 31) / 32, (p.sy + 7) / 8);
+	k_integrate_plan<<<grid, block, 0, c->stream>>>(p);
+	LAUNCHED(c);
+	k_integrate_run<<<c->int_grid, 256, 0, c->stream>>>(p);
 	LAUNCHED(c);
 	CK(cudaGetLastError());
 	c->integrate_count++;

@@ -506,111 +506,187 @@ struct IntegrateParams {
 	const float* dmax;         // optional: max of the depth image (device scalar); nullptr = unknown
 	int cull;                  // 0 = visit every voxel (debug / A-B), 1 = interval + fast tests
 	unsigned long long* n_upd;
+	uint2* queue;              // work list: pieces of warp-column intervals
+	unsigned int* queue_count; // [0] items appended by the plan pass, [1] next item (this frame's slot)
+	unsigned int* queue_head;
+	unsigned int* queue_next;  // the other slot's two counters, zeroed by the plan pass for the next frame
 };
 
-// tighten [tlo, thi] with the constraint a + b*t >= -s (NaNs never tighten)
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, <= 1 ulp, no denormal handling
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+// packed fp32 pair add (Blackwell FADD2: one issue slot for two IEEE additions)
+struct F2 { unsigned long long v; };
+__device__ __forceinline__ F2 f2_make(float lo, float hi) {
+	F2 r;
+	r.v = ((unsigned long long) __float_as_uint(hi) << 32) | (unsigned long long) __float_as_uint(lo);
+	return r;
+}
+__device__ __forceinline__ float f2_lo(F2 a) { return __uint_as_float((unsigned int) a.v); }
+__device__ __forceinline__ float f2_hi(F2 a) { return __uint_as_float((unsigned int) (a.v >> 32)); }
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+	F2 r;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+	return r;
+}
+
+// tighten [tlo, thi] with the constraint a + b*t >= -s.  Approximate division: the caller widens the
+// result by a whole voxel.  NaNs never tighten; b == 0 decides on a alone.
 __device__ __forceinline__ void clip_line(float a, float b, float s, float& tlo, float& thi) {
-	const float r = (-s - a) / b;   // b == 0 -> +-inf or NaN, handled below
+	const float r = (-s - a) * rcp_approx(b);
 	if (b > 0.f) { if (r > tlo) tlo = r; }
 	else if (b < 0.f) { if (r < thi) thi = r; }
 	else if (a < -s) { tlo = 1.f; thi = 0.f; }
 }
 
-__global__ void __launch_bounds__(256) k_integrate(IntegrateParams p) {
+// the reference's full per-voxel expression (cpp/kernels.cpp:647-661): returns sdf, or -4 for "no update"
+__device__ __noinline__ float integrate_exact(float Px, float Py, float Pz, float Cx, float Cy, float Cz, const float* __restrict__ depth,
+		uint32_t dw, float dwm1, float dhm1, float mu) {
+	const float pxf = Cx / Cz + 0.5f, pyf = Cy / Cz + 0.5f;
+	if (pxf < 0 || pxf > dwm1 || pyf < 0 || pyf > dhm1) return -4.f;
+	const uint32_t px = (uint32_t) pxf, py = (uint32_t) pyf;
+	const float d = __ldg(depth + (px + py * dw));
+	if (d == 0) return -4.f;
+	const float diff = (d - Cz) * sqrtf(1 + ksq(Px / Pz) + ksq(Py / Pz));
+	if (diff > -mu) return kminf(1.f, diff / mu);
+	return -4.f;
+}
+// same, for a voxel whose pixel is already known exactly: only the sdf part (:655-661); e = depth[px] - cameraX.z
+__device__ __noinline__ float integrate_exact_sdf(float Px, float Py, float Pz, float e, float mu) {
+	const float diff = e * sqrtf(1 + ksq(Px / Pz) + ksq(Py / Pz));
+	if (diff > -mu) return kminf(1.f, diff / mu);
+	return -4.f;
+}
+
+// per-column state at z = 0 (cpp/kernels.cpp:638-644) and the conservative visited interval of one column
+struct IntColumn { float3 pos0, cam0, delta, cameraDelta; };
+__device__ __forceinline__ IntColumn int_column(const IntegrateParams& p, uint32_t x, uint32_t y) {
+	IntColumn c;
+	c.delta = mat_rotate(p.invTrack, f3(0, 0, p.dz / (float) p.sz));
+	c.cameraDelta = mat_rotate(p.K, c.delta);
+	// Volume::pos (commons.h:186-189) at z = 0
+	c.pos0 = mat_point(p.invTrack, f3(((float) x + 0.5f) * p.dx / (float) p.sx, ((float) y + 0.5f) * p.dy / (float) p.sy,
+			(0 + 0.5f) * p.dz / (float) p.sz));
+	c.cam0 = mat_point(p.K, c.pos0);
+	return c;
+}
+
+// Pass 1: one warp per 32 x-adjacent columns: conservative interval, cut into pieces of `zchunk` slices,
+// appended to the work list.  item = { xtile | y << 16, z_start | len << 16 }.
+__global__ void __launch_bounds__(256) k_integrate_plan(IntegrateParams p) {
 	const uint32_t x = blockIdx.x * 32 + threadIdx.x;
 	const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;   // warp-uniform
-	const uint32_t zs = p.z_begin + blockIdx.z * p.zchunk;
-	const uint32_t ze = min(zs + p.zchunk, p.z_end);
-	const bool valid = x < p.sx && y < p.sy && zs < ze;
-	unsigned int updated = 0;
-
-	const float3 delta = mat_rotate(p.invTrack, f3(0, 0, p.dz / (float) p.sz));
-	const float3 cameraDelta = mat_rotate(p.K, delta);
-	// Volume::pos (commons.h:186-189) at z = 0
-	float3 pos = mat_point(p.invTrack, f3(((float) x + 0.5f) * p.dx / (float) p.sx, ((float) y + 0.5f) * p.dy / (float) p.sy,
-			(0 + 0.5f) * p.dz / (float) p.sz));
-	float3 cameraX = mat_point(p.K, pos);
-	const float dwm1 = (float) (p.dw - 1), dhm1 = (float) (p.dh - 1);
-
-	int za = (int) zs, zb = (int) ze;
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) { p.queue_next[0] = 0u; p.queue_next[1] = 0u; }  // re-arm the other slot
+	const bool valid = x < p.sx && y < p.sy;
+	int za = (int) p.z_begin, zb = (int) p.z_end;
 	if (!valid) { za = 0x7fffffff; zb = 0; }
 	else if (p.cull) {
+		const IntColumn c = int_column(p, x, y);
+		const float3 pos0 = c.pos0, cam0 = c.cam0, delta = c.delta, cameraDelta = c.cameraDelta;
+		const float dwm1 = (float) (p.dw - 1), dhm1 = (float) (p.dh - 1);
 		// conservative interval on the un-rounded line; slack = bound on the accumulated rounding error
 		const float n = (float) p.sz;
-		const float Mx = kmaxf(fabsf(cameraX.x), fabsf(cameraX.x + n * cameraDelta.x));
-		const float My = kmaxf(fabsf(cameraX.y), fabsf(cameraX.y + n * cameraDelta.y));
-		const float Mz = kmaxf(fabsf(cameraX.z), fabsf(cameraX.z + n * cameraDelta.z));
-		const float Mp = kmaxf(fabsf(pos.z), fabsf(pos.z + n * delta.z));
+		const float Mx = kmaxf(fabsf(cam0.x), fabsf(cam0.x + n * cameraDelta.x));
+		const float My = kmaxf(fabsf(cam0.y), fabsf(cam0.y + n * cameraDelta.y));
+		const float Mz = kmaxf(fabsf(cam0.z), fabsf(cam0.z + n * cameraDelta.z));
+		const float Mp = kmaxf(fabsf(pos0.z), fabsf(pos0.z + n * delta.z));
 		const float eps = (n + 64.f) * 2.3841858e-7f;   // (N + 64) * 2^-22: > 2x the worst-case drift of N additions
 		const float wq = dwm1 - 0.5f, hq = dhm1 - 0.5f;
 		float tlo = -1e9f, thi = 1e9f;
-		clip_line(pos.z - 0.0001f, delta.z, eps * Mp, tlo, thi);                                                   // pos.z >= 1e-4
-		clip_line(cameraX.x + 0.5f * cameraX.z, cameraDelta.x + 0.5f * cameraDelta.z, eps * (Mx + Mz), tlo, thi);   // px >= 0
-		clip_line(wq * cameraX.z - cameraX.x, wq * cameraDelta.z - cameraDelta.x, eps * (Mx + (wq + 2.f) * Mz), tlo, thi);  // px <= w-1
-		clip_line(cameraX.y + 0.5f * cameraX.z, cameraDelta.y + 0.5f * cameraDelta.z, eps * (My + Mz), tlo, thi);   // py >= 0
-		clip_line(hq * cameraX.z - cameraX.y, hq * cameraDelta.z - cameraDelta.y, eps * (My + (hq + 2.f) * Mz), tlo, thi);  // py <= h-1
+		clip_line(pos0.z - 0.0001f, delta.z, eps * Mp, tlo, thi);                                            // pos.z >= 1e-4
+		clip_line(cam0.x + 0.5f * cam0.z, cameraDelta.x + 0.5f * cameraDelta.z, eps * (Mx + Mz), tlo, thi);   // px >= 0
+		clip_line(wq * cam0.z - cam0.x, wq * cameraDelta.z - cameraDelta.x, eps * (Mx + (wq + 2.f) * Mz), tlo, thi);  // px <= w-1
+		clip_line(cam0.y + 0.5f * cam0.z, cameraDelta.y + 0.5f * cameraDelta.z, eps * (My + Mz), tlo, thi);   // py >= 0
+		clip_line(hq * cam0.z - cam0.y, hq * cameraDelta.z - cameraDelta.y, eps * (My + (hq + 2.f) * Mz), tlo, thi);  // py <= h-1
 		if (p.dmax) {
 			// no update unless depth - cameraX.z > -mu  (lambda >= 1)  =>  cameraX.z < max(depth) + mu
 			const float far = *p.dmax + p.mu;
-			if (far == far) clip_line(far - cameraX.z, -cameraDelta.z, eps * Mz + 1e-6f * fabsf(far), tlo, thi);
+			if (far == far) clip_line(far - cam0.z, -cameraDelta.z, eps * Mz + 1e-6f * fabsf(far), tlo, thi);
 		}
 		if (tlo > thi) { za = 0x7fffffff; zb = 0; }
 		else {
-			const float lo = floorf(tlo) - 1.f, hi = ceilf(thi) + 2.f;
+			const float lo = floorf(tlo) - 2.f, hi = ceilf(thi) + 3.f;   // approximate quotient + rounding: a voxel each side
 			if (lo > (float) za) za = (lo < 2e9f) ? (int) lo : 0x7fffffff;
 			if (hi < (float) zb) zb = (hi > -2e9f) ? (int) hi : 0;
 		}
 	}
 	za = __reduce_min_sync(0xffffffffu, za);
 	zb = __reduce_max_sync(0xffffffffu, zb);
+	if (za >= zb) return;
+	const uint32_t pieces = ((uint32_t) (zb - za) + p.zchunk - 1) / p.zchunk;
+	uint32_t base = 0;
+	if (threadIdx.x == 0) base = atomicAdd(p.queue_count, pieces);
+	base = __shfl_sync(0xffffffffu, base, 0);
+	for (uint32_t i = threadIdx.x; i < pieces; i += 32) {
+		const uint32_t z0 = (uint32_t) za + i * p.zchunk;
+		const uint32_t len = min(p.zchunk, (uint32_t) zb - z0);
+		p.queue[base + i] = make_uint2(blockIdx.x | (y << 16), z0 | (len << 16));
+	}
+}
 
-	if (za < zb) {
+// Pass 2: persistent warps pull pieces from the work list (dynamic balance: no empty warps, no tail).
+__global__ void __launch_bounds__(256, 4) k_integrate_run(IntegrateParams p) {
+	const uint32_t lane = threadIdx.x & 31;
+	const float dwm1 = (float) (p.dw - 1), dhm1 = (float) (p.dh - 1);
+	// fast tests need: mu > 0, image small enough that an approximate quotient beyond +-2048 is conclusively outside
+	const bool fast = p.cull && p.mu > 0.f && p.dw <= 2040 && p.dh <= 2040;
+	// |approximate - exact| <= |q| 2^-22 + ulp: scale the "too close to an integer" band with the image size
+	const float tol = (float) max(p.dw, p.dh) * 4.0e-7f + 1.0e-5f;
+	const float mu = p.mu;
+	const float* __restrict__ depth = p.depth;
+	const uint32_t dw = p.dw;
+	const size_t plane = (size_t) p.sx * p.sy;
+	const unsigned int count = *p.queue_count;
+	unsigned int updated = 0;
+
+	for (;;) {
+		unsigned int it = 0;
+		if (lane == 0) it = atomicAdd(p.queue_head, 1u);
+		it = __shfl_sync(0xffffffffu, it, 0);
+		if (it >= count) break;
+		const uint2 item = __ldcg(p.queue + it);
+		const uint32_t x = (item.x & 0xffffu) * 32 + lane, y = item.x >> 16;
+		const int za = (int) (item.y & 0xffffu), zb = za + (int) (item.y >> 16);
+		const bool valid = x < p.sx;
+		const IntColumn c = int_column(p, x, y);
+		// running values, packed in pairs: (pos.x, pos.y) (pos.z, cam.x) (cam.y, cam.z)
+		F2 A = f2_make(c.pos0.x, c.pos0.y), B = f2_make(c.pos0.z, c.cam0.x), C = f2_make(c.cam0.y, c.cam0.z);
+		const F2 dA = f2_make(c.delta.x, c.delta.y), dB = f2_make(c.delta.z, c.cameraDelta.x), dC = f2_make(c.cameraDelta.y, c.cameraDelta.z);
 		// replay the reference's additions up to the first visited slice
 #pragma unroll 8
-		for (int z = 0; z < za; ++z) { pos = pos + delta; cameraX = cameraX + cameraDelta; }
-		const size_t plane = (size_t) p.sx * p.sy;
+		for (int z = 0; z < za; ++z) { A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC); }
 		short2* col = p.vol + (size_t) x + (size_t) y * p.sx + (size_t) ((uint32_t) za - p.z_begin) * plane;
-		const bool fast = p.cull && p.mu > 0.f && p.dw <= 2048 && p.dh <= 2048;
-		const float mu = p.mu;
-		// INT_U consecutive slices per batch: all decisions first (depth gathers hit L1/L2), then all
-		// voxel loads back to back (INT_U independent 128-byte requests in flight per warp: the
+		// INT_U consecutive slices per batch: all decisions first, straight-line (depth gathers hit L1/L2), then
+		// all voxel loads back to back (INT_U independent 128-byte requests in flight per warp: the
 		// read-modify-write is latency-bound otherwise), then the updates and stores.
 		for (int z = za; z < zb; z += INT_U, col += INT_U * plane) {
 			float sdf[INT_U];
 			short2 v[INT_U];
 #pragma unroll
 			for (int u = 0; u < INT_U; ++u) {
-				sdf[u] = -4.f;   // "no update" (a real sdf is > -1)
-				const float3 P = pos, C = cameraX;
-				pos = pos + delta; cameraX = cameraX + cameraDelta;
-				if (!valid || z + u >= zb) continue;
-				if (P.z < 0.0001f) continue;
-				float pxf, pyf;
+				const float Px = f2_lo(A), Py = f2_hi(A), Pz = f2_lo(B), Cx = f2_hi(B), Cy = f2_lo(C), Cz = f2_hi(C);
+				A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC);
+				const bool act = valid && (z + u < zb) && !(Pz < 0.0001f);
+				float s = -4.f;   // "no update" (a real sdf is > -1)
 				if (fast) {
-					pxf = __fdividef(C.x, C.z) + 0.5f;
-					pyf = __fdividef(C.y, C.z) + 0.5f;
-					// |approximate - exact| < 1e-3 for |q| < 2048: the truncated pixel and the bounds tests (integers
-					// 0, w-1, h-1) can only differ when the value is that close to an integer
-					if (fabsf(pxf - rintf(pxf)) < 1e-3f || fabsf(pyf - rintf(pyf)) < 1e-3f || !(fabsf(pxf) < 2048.f) || !(fabsf(pyf) < 2048.f)) {
-						pxf = C.x / C.z + 0.5f;
-						pyf = C.y / C.z + 0.5f;
-					}
-				} else {
-					pxf = C.x / C.z + 0.5f;
-					pyf = C.y / C.z + 0.5f;
-				}
-				if (pxf < 0 || pxf > dwm1 || pyf < 0 || pyf > dhm1) continue;
-				const uint32_t px = (uint32_t) pxf, py = (uint32_t) pyf;
-				const float d = __ldg(p.depth + px + (size_t) py * p.dw);
-				if (d == 0) continue;
-				const float e = d - C.z;
-				if (fast && e > mu) sdf[u] = 1.f;
-				else if (fast && e < -mu) continue;
-				else {
-					const float diff = e * sqrtf(1 + ksq(P.x / P.z) + ksq(P.y / P.z));
-					if (!(diff > -mu)) continue;
-					sdf[u] = kminf(1.f, diff / mu);
-				}
+					const float r = rcp_approx(Cz);
+					const float pxf = Cx * r + 0.5f, pyf = Cy * r + 0.5f;
+					// the truncated pixel and the bounds tests (against the integers 0, w-1, h-1) can only differ from
+					// the exact ones when the value is within `tol` of an integer.  NaN/inf fail both comparisons.
+					const bool sure = (fabsf(pxf - rintf(pxf)) >= tol) && (fabsf(pyf - rintf(pyf)) >= tol);
+					const bool inb = !(pxf < 0 || pxf > dwm1 || pyf < 0 || pyf > dhm1);
+					const uint32_t idx = inb ? ((uint32_t) pxf + (uint32_t) pyf * dw) : 0u;
+					const float d = __ldg(depth + idx);
+					const float e = d - Cz;
+					// sure & inside: e > mu => sdf == 1 exactly; e < -mu or d == 0 => no update (header comment);
+					// sure & outside: no update; |e| <= mu: the reference's sqrt/division expression; not sure: all of it
+					if (act && sure && inb && e > mu && d != 0) s = 1.f;
+					if (act && sure && inb && d != 0 && !(e > mu) && !(e < -mu)) s = integrate_exact_sdf(Px, Py, Pz, e, mu);
+					if (act && !sure) s = integrate_exact(Px, Py, Pz, Cx, Cy, Cz, depth, dw, dwm1, dhm1, mu);
+				} else if (act) s = integrate_exact(Px, Py, Pz, Cx, Cy, Cz, depth, dw, dwm1, dhm1, mu);
+				sdf[u] = s;
 			}
 #pragma unroll
 			for (int u = 0; u < INT_U; ++u)
@@ -628,7 +704,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntegrateParams p) {
 	}
 	// exact N_upd: one atomic per warp
 	updated = __reduce_add_sync(0xffffffffu, updated);
-	if ((threadIdx.x & 31) == 0 && updated) atomicAdd(p.n_upd, (unsigned long long) updated);
+	if (lane == 0 && updated) atomicAdd(p.n_upd, (unsigned long long) updated);
 }
 
 // ------------------------------------------------------------------------------------------
