@@ -1,0 +1,157 @@
+// kfusion-b200: the drop-in backend glue.
+//
+// The reference selects its KinectFusion backend at LINK time: kfusion-benchmark-<v> is
+// benchmark.cpp + PowerMonitor.cpp linked against a library that defines the out-of-line members
+// of `class Kfusion` declared in kfusion/include/kernels.h:83-195 (CMakeLists.txt:53-54,
+// kfusion/CMakeLists.txt:40-75).  This translation unit is that library for the B200 backend: it
+// is compiled against the reference's UNMODIFIED kernels.h and forwards every member to the C ABI
+// of libkfb200.so (include/kfb200.h).  No kernel code lives here, and nothing here falls back to
+// the CPU: a failing kfb_* call prints the library's message and exit(1)s, which is the
+// reference's own error convention (cuda/kernels.cu:675-678, cpp/kernels.cpp:566-577).
+//
+// The class layout is frozen by the header (no room for a handle member) and the reference
+// backends keep their state in file-scope globals; we keep a `this`-keyed table instead so that
+// several Kfusion objects can coexist.
+#include <kernels.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+
+#include "kfb200.h"
+
+namespace {
+
+std::map<const void*, kfb_ctx*>& table() {
+	static std::map<const void*, kfb_ctx*> t;
+	return t;
+}
+
+kfb_ctx* ctx_of(const void* self) {
+	std::map<const void*, kfb_ctx*>::iterator it = table().find(self);
+	if (it == table().end()) {
+		std::fprintf(stderr, "kfusion-b200: Kfusion object %p has no device context\n", self);
+		std::exit(1);
+	}
+	return it->second;
+}
+
+void check(int rc, const char* what) {
+	if (rc == 0) return;
+	std::fprintf(stderr, "kfusion-b200: %s failed (%d): %s\n", what, rc, kfb_last_error());
+	std::exit(1);
+}
+
+inline void k4(const float4& k, float out[4]) { out[0] = k.x; out[1] = k.y; out[2] = k.z; out[3] = k.w; }
+
+}  // namespace
+
+// kernels.h:140 — called at the end of both inline constructors, after computationSize, pose,
+// volumeDimensions, volumeResolution, iterations, step and viewPose are set (kernels.h:99-138)
+void Kfusion::languageSpecificConstructor() {
+	kfb_config cfg;
+	std::memset(&cfg, 0, sizeof cfg);
+	cfg.compute_w = computationSize.x;
+	cfg.compute_h = computationSize.y;
+	cfg.volume_res[0] = volumeResolution.x; cfg.volume_res[1] = volumeResolution.y; cfg.volume_res[2] = volumeResolution.z;
+	cfg.volume_dim[0] = volumeDimensions.x; cfg.volume_dim[1] = volumeDimensions.y; cfg.volume_dim[2] = volumeDimensions.z;
+	std::memcpy(cfg.init_pose, &pose, sizeof cfg.init_pose);   // Matrix4 = 4 x float4, row-major (commons.h:317-319)
+	if (iterations.size() > KFB_MAX_LEVELS) {
+		std::fprintf(stderr, "kfusion-b200: at most %d pyramid levels\n", KFB_MAX_LEVELS);
+		std::exit(1);
+	}
+	cfg.n_levels = (int32_t) iterations.size();
+	for (size_t i = 0; i < iterations.size(); ++i) cfg.iterations[i] = iterations[i];
+	const char* dev = std::getenv("KFB_DEVICE");
+	cfg.device = dev ? std::atoi(dev) : 0;
+	// benchmark.cpp:153-156 renders the ICP status map every frame: keep the 1-byte status plane
+	cfg.flags = std::getenv("KFB_NO_TRACK_STATUS") ? 0u : KFB_FLAG_TRACK_STATUS;
+	if (std::getenv("KFB_ICP_HOST_SOLVE")) cfg.flags |= KFB_FLAG_ICP_HOST_SOLVE;
+	kfb_ctx* c = NULL;
+	check(kfb_create(&cfg, &c), "kfb_create");
+	table()[this] = c;
+	_tracked = false;
+	_integrated = false;
+}
+
+Kfusion::~Kfusion() {
+	std::map<const void*, kfb_ctx*>::iterator it = table().find(this);
+	if (it != table().end()) {
+		kfb_destroy(it->second);
+		table().erase(it);
+	}
+}
+
+void Kfusion::reset() { check(kfb_reset(ctx_of(this)), "kfb_reset"); }
+
+bool Kfusion::preprocessing(const ushort* inputDepth, const uint2 inputSize) {
+	check(kfb_preprocess(ctx_of(this), inputDepth, inputSize.x, inputSize.y), "kfb_preprocess");
+	return true;
+}
+
+bool Kfusion::tracking(float4 k, float icp_threshold, uint tracking_rate, uint frame) {
+	kfb_ctx* c = ctx_of(this);
+	float kk[4];
+	k4(k, kk);
+	int tracked = 0;
+	check(kfb_track(c, kk, icp_threshold, tracking_rate, frame, &tracked), "kfb_track");
+	// getPose() is inline and reads the member (kernels.h:173-175; benchmark.cpp:127)
+	check(kfb_get_pose(c, reinterpret_cast<float*>(&pose)), "kfb_get_pose");
+	return tracked != 0;
+}
+
+bool Kfusion::raycasting(float4 k, float mu, uint frame) {
+	float kk[4];
+	k4(k, kk);
+	check(kfb_raycast(ctx_of(this), kk, mu, frame), "kfb_raycast");
+	return false;   // the reference's doRaycast is never set (cpp/kernels.cpp:975-984)
+}
+
+bool Kfusion::integration(float4 k, uint integration_rate, float mu, uint frame) {
+	kfb_ctx* c = ctx_of(this);
+	float kk[4];
+	k4(k, kk);
+	int integrated = 0;
+	check(kfb_integrate(c, kk, integration_rate, mu, frame, &integrated), "kfb_integrate");
+	// checkPoseKernel may have restored oldPose (cpp/kernels.cpp:991)
+	check(kfb_get_pose(c, reinterpret_cast<float*>(&pose)), "kfb_get_pose");
+	return integrated != 0;
+}
+
+void Kfusion::computeFrame(const ushort* inputDepth, const uint2 inputSize, float4 k, uint integration_rate, uint tracking_rate,
+		float icp_threshold, float mu, const uint frame) {
+	preprocessing(inputDepth, inputSize);
+	_tracked = tracking(k, icp_threshold, tracking_rate, frame);
+	_integrated = integration(k, integration_rate, mu, frame);
+	raycasting(k, mu, frame);
+}
+
+void Kfusion::dumpVolume(const char* filename) {
+	if (filename == NULL) return;
+	check(kfb_dump_volume(ctx_of(this), filename), "kfb_dump_volume");
+}
+
+void Kfusion::renderVolume(uchar4* out, const uint2 outputSize, int frame, int rate, float4 k, float largestep) {
+	float kk[4];
+	k4(k, kk);
+	check(kfb_render_volume(ctx_of(this), reinterpret_cast<uint8_t*>(out), outputSize.x, outputSize.y, frame, rate, kk, largestep,
+			reinterpret_cast<const float*>(viewPose)), "kfb_render_volume");
+}
+
+void Kfusion::renderTrack(uchar4* out, const uint2 outputSize) {
+	check(kfb_render_track(ctx_of(this), reinterpret_cast<uint8_t*>(out), outputSize.x, outputSize.y), "kfb_render_track");
+}
+
+void Kfusion::renderDepth(uchar4* out, uint2 outputSize) {
+	check(kfb_render_depth(ctx_of(this), reinterpret_cast<uint8_t*>(out), outputSize.x, outputSize.y), "kfb_render_depth");
+}
+
+// kernels.h:197 — benchmark.cpp:26-27 calls this before every timestamp
+void synchroniseDevices() {
+	for (std::map<const void*, kfb_ctx*>::iterator it = table().begin(); it != table().end(); ++it) kfb_sync(it->second);
+}
+
+// kernels.h:77-79 (declared for the GUI front-ends; nothing to do: contexts are per object)
+void init() {}
+void clean() {}

@@ -1,0 +1,54 @@
+"""The drop-in binary: the reference's UNMODIFIED benchmark.cpp linked against the B200 backend glue
+(slambench_b200/csrc/kfusion_b200.cpp -> libkfb200.so), run on a synthetic `.raw` next to the
+reference's own kfusion-benchmark-cpp (oracle/_ref) with identical flags.  Both binaries are built
+in the container that has /root/reference and travel to the GPU box; nothing here reads the reference tree."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from slambench_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+B200_BIN = os.path.join(ROOT, "build", "kfusion-benchmark-b200")
+CPP_BIN = os.path.join(ROOT, "oracle", "_ref", "kfusion-benchmark-cpp")
+
+
+def parse_log(path):
+    rows = []
+    for line in open(path):
+        t = line.split()
+        if len(t) == 14 and t[0].isdigit():
+            rows.append([float(v) for v in t])
+    return np.array(rows)
+
+
+@pytest.mark.skipif(not (os.path.exists(B200_BIN) and os.path.exists(CPP_BIN)), reason="benchmark binaries not built (need /root/reference at build time)")
+def test_drop_in_benchmark_matches_reference_binary(tmp_path):
+    n, vres = 14, 96
+    depth, _ = synth.make_sequence(n)
+    raw = str(tmp_path / "seq.raw")
+    synth.write_raw(raw, depth)
+    logs, dumps = {}, {}
+    for name, exe in (("b200", B200_BIN), ("cpp", CPP_BIN)):
+        log, dump = str(tmp_path / f"{name}.log"), str(tmp_path / f"{name}.vol")
+        cmd = [exe, "-i", raw, "-s", "4.8", "-p", "0.5,0.5,0.25", "-z", "4", "-c", "1", "-r", "1", "-t", "1", "-m", "0.1", "-y", "10,5,4",
+               "-l", "1e-5", "-k", "481.2,480,320,240", "-v", str(vres), "-o", log, "-d", dump]
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+        logs[name], dumps[name] = parse_log(log), np.fromfile(dump, dtype=np.int16)
+    a, b = logs["b200"], logs["cpp"]
+    assert a.shape == b.shape == (n, 14)
+    assert np.array_equal(a[:, 12:], b[:, 12:]), "tracked / integrated columns differ"
+    assert list(b[:, 12]) == [0] * 4 + [1] * (n - 4)
+    assert np.abs(a[:, 9:12] - b[:, 9:12]).max() <= 1e-4, "logged X,Y,Z differ"
+    # -d dump: tsdf shorts only, x fastest (cpp/kernels.cpp:1006-1030)
+    assert dumps["b200"].size == dumps["cpp"].size == vres ** 3
+    d = np.abs(dumps["b200"].astype(np.int32) - dumps["cpp"].astype(np.int32))
+    assert (d <= 1).mean() > 0.999
+    # and it is fast: the computation column (benchmark.cpp:166) of the tracked frames
+    assert a[4:, 7].mean() < b[4:, 7].mean() / 20
