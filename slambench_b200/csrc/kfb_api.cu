@@ -138,6 +138,28 @@ static void timer_free(StageTimer& t) {
 	t.pending.clear(); t.pool.clear();
 }
 
+// Is q = a*rd, q + fma(-d,q,a)*rd == a/d for EVERY float a (all 2^23 significands, two binades)?  Checked once per
+// divisor on the host (fmaf is exact); the raycaster then divides by the volume dimensions in 3 instructions.
+static int kfb_fastdiv_ok(float d) {
+	static float cache_d[8]; static int cache_r[8]; static int n_cache = 0;
+	for (int i = 0; i < n_cache; ++i) if (cache_d[i] == d) return cache_r[i];
+	int ok = (d == d) && d > 1e-20f && d < 1e20f;
+	if (ok) {
+		const float rd = 1.0f / d;
+		for (uint32_t e = 127; e <= 128 && ok; ++e)
+			for (uint32_t m = 0; m < (1u << 23); ++m) {
+				const uint32_t u = (e << 23) | m;
+				float a;
+				memcpy(&a, &u, 4);
+				const float q = a * rd;
+				const float q1 = fmaf(fmaf(-d, q, a), rd, q);
+				if (q1 != a / d) { ok = 0; break; }
+			}
+	}
+	if (n_cache < 8) { cache_d[n_cache] = d; cache_r[n_cache] = ok; ++n_cache; }
+	return ok;
+}
+
 static inline Mat4 toMat(const float* m) { Mat4 r; memcpy(r.m, m, sizeof r.m); return r; }
 #define LAUNCHED(c) ((c)->st.kernel_launches++)
 
@@ -282,6 +304,8 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	c->view_all.slab_z[0] = c->z0; c->view_all.slab_z[1] = c->z1;
 	c->view_all.sx = cfg->volume_res[0]; c->view_all.sy = cfg->volume_res[1]; c->view_all.sz = cfg->volume_res[2];
 	c->view_all.dx = cfg->volume_dim[0]; c->view_all.dy = cfg->volume_dim[1]; c->view_all.dz = cfg->volume_dim[2];
+	c->view_all.rdx = 1.0f / cfg->volume_dim[0]; c->view_all.rdy = 1.0f / cfg->volume_dim[1]; c->view_all.rdz = 1.0f / cfg->volume_dim[2];
+	c->view_all.fastdiv = (kfb_fastdiv_ok(cfg->volume_dim[0]) && kfb_fastdiv_ok(cfg->volume_dim[1]) && kfb_fastdiv_ok(cfg->volume_dim[2])) ? 1 : 0;
 	for (int i = 0; i < KFB_MAX_SLABS; ++i) c->peer_ptrs[i] = nullptr;
 	int rc = launch_init_volume(c);
 	if (rc) return rc;
@@ -647,7 +671,7 @@ static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP
 	p.row0 = 0; p.row1 = c->ch;
 	p.view = toMat(view);
 	p.nearPlane = nearP; p.farPlane = farP; p.step = step; p.largestep = largestep;
-	dim3 block(RC_BX, RC_BY), grid((p.w + RC_BX - 1) / RC_BX, (p.row1 - p.row0 + RC_BY - 1) / RC_BY);
+	dim3 block(RCK_BX * RCK_BY), grid((p.w + RCK_BX - 1) / RCK_BX, (p.row1 - p.row0 + RCK_BY - 1) / RCK_BY);
 	k_raycast<<<grid, block, 0, c->stream>>>(p);
 	LAUNCHED(c);
 	CK(cudaGetLastError());

@@ -721,7 +721,21 @@ struct VolView {
 	int n_slabs;
 	uint32_t sx, sy, sz;
 	float dx, dy, dz;
+	// 1/dim (correctly rounded) and "the 3-instruction division by this constant is exact" (verified exhaustively
+	// over all 2^23 significands on the host at kfb_create, see kfb_fastdiv_ok)
+	float rdx, rdy, rdz;
+	int fastdiv;
 };
+
+// fl(a / d) for a per-launch constant d with rd = fl(1/d): q = a*rd, r = fma(-d, q, a) (exact), q + r*rd rounds
+// correctly (Markstein).  Only used when the host verified it for this d; out-of-range a takes the IEEE path.
+__device__ __forceinline__ float div_const(float a, float d, float rd, int ok) {
+	if (ok && fabsf(a) < 1e30f && fabsf(a) > 1e-30f) {
+		const float q = a * rd;
+		return __fmaf_rn(__fmaf_rn(-d, q, a), rd, q);
+	}
+	return a / d;
+}
 
 __device__ __forceinline__ float vol_vs2(const VolView& v, int x, int y, int z) {  // commons.h:172-174
 	int s = 0;
@@ -734,21 +748,40 @@ __device__ __forceinline__ float vol_vs2(const VolView& v, int x, int y, int z) 
 	return (float) __ldg(reinterpret_cast<const short*>(base + idx));
 }
 
+__device__ __forceinline__ const short2* vol_plane(const VolView& v, int z) {   // first voxel of slice z (maybe in a peer's slab)
+	int s = 0;
+	if (v.n_slabs > 1) {
+#pragma unroll
+		for (int i = 1; i < KFB_MAX_SLABS; ++i) s += (i < v.n_slabs && (uint32_t) z >= v.slab_z[i]);
+	}
+	return v.slab_ptr[s] + (size_t) ((uint32_t) z - v.slab_z[s]) * v.sx * v.sy;
+}
+
 __device__ __forceinline__ float vol_interp(const VolView& v, float3 pos) {  // commons.h:191-213
-	const float3 sp = f3((pos.x * (float) v.sx / v.dx) - 0.5f, (pos.y * (float) v.sy / v.dy) - 0.5f, (pos.z * (float) v.sz / v.dz) - 0.5f);
-	const float flx = floorf(sp.x), fly = floorf(sp.y), flz = floorf(sp.z);
+	const float spx = div_const(pos.x * (float) v.sx, v.dx, v.rdx, v.fastdiv) - 0.5f;
+	const float spy = div_const(pos.y * (float) v.sy, v.dy, v.rdy, v.fastdiv) - 0.5f;
+	const float spz = div_const(pos.z * (float) v.sz, v.dz, v.rdz, v.fastdiv) - 0.5f;
+	const float flx = floorf(spx), fly = floorf(spy), flz = floorf(spz);
 	const int bx = (int) flx, by = (int) fly, bz = (int) flz;
-	const float3 f = f3(sp.x - flx, sp.y - fly, sp.z - flz);
+	const float fx = spx - flx, fy = spy - fly, fz = spz - flz;
 	const int lx = kmaxi(bx, 0), ly = kmaxi(by, 0), lz = kmaxi(bz, 0);
 	const int ux = kmini(bx + 1, (int) v.sx - 1), uy = kmini(by + 1, (int) v.sy - 1), uz = kmini(bz + 1, (int) v.sz - 1);
-	return (((vol_vs2(v, lx, ly, lz) * (1 - f.x) + vol_vs2(v, ux, ly, lz) * f.x) * (1 - f.y)
-			+ (vol_vs2(v, lx, uy, lz) * (1 - f.x) + vol_vs2(v, ux, uy, lz) * f.x) * f.y) * (1 - f.z)
-			+ ((vol_vs2(v, lx, ly, uz) * (1 - f.x) + vol_vs2(v, ux, ly, uz) * f.x) * (1 - f.y)
-					+ (vol_vs2(v, lx, uy, uz) * (1 - f.x) + vol_vs2(v, ux, uy, uz) * f.x) * f.y) * f.z) * 0.00003051944088f;
+	// two slice bases (z may straddle slabs), two row offsets, two column offsets: 8 taps from 3 adds each
+	const short2* pl = vol_plane(v, lz);
+	const short2* pu = (v.n_slabs > 1) ? vol_plane(v, uz) : pl + (size_t) (uz - lz) * v.sx * v.sy;
+	const uint32_t rl = (uint32_t) ly * v.sx, ru = (uint32_t) uy * v.sx;
+#define TAP(P, R, X) ((float) __ldg(reinterpret_cast<const short*>((P) + ((R) + (uint32_t) (X)))))
+	const float v000 = TAP(pl, rl, lx), v100 = TAP(pl, rl, ux), v010 = TAP(pl, ru, lx), v110 = TAP(pl, ru, ux);
+	const float v001 = TAP(pu, rl, lx), v101 = TAP(pu, rl, ux), v011 = TAP(pu, ru, lx), v111 = TAP(pu, ru, ux);
+#undef TAP
+	const float gx = 1 - fx, gy = 1 - fy, gz = 1 - fz;
+	return (((v000 * gx + v100 * fx) * gy + (v010 * gx + v110 * fx) * fy) * gz
+			+ ((v001 * gx + v101 * fx) * gy + (v011 * gx + v111 * fx) * fy) * fz) * 0.00003051944088f;
 }
 
 __device__ __forceinline__ float3 vol_grad(const VolView& v, float3 pos) {  // commons.h:215-301
-	const float3 sp = f3((pos.x * (float) v.sx / v.dx) - 0.5f, (pos.y * (float) v.sy / v.dy) - 0.5f, (pos.z * (float) v.sz / v.dz) - 0.5f);
+	const float3 sp = f3(div_const(pos.x * (float) v.sx, v.dx, v.rdx, v.fastdiv) - 0.5f, div_const(pos.y * (float) v.sy, v.dy, v.rdy, v.fastdiv) - 0.5f,
+			div_const(pos.z * (float) v.sz, v.dz, v.rdz, v.fastdiv) - 0.5f);
 	const float flx = floorf(sp.x), fly = floorf(sp.y), flz = floorf(sp.z);
 	const int bx = (int) flx, by = (int) fly, bz = (int) flz;
 	const float3 f = f3(sp.x - flx, sp.y - fly, sp.z - flz);
@@ -823,9 +856,13 @@ struct RaycastParams {
 
 #define RC_BX 16
 #define RC_BY 16
-__global__ void __launch_bounds__(RC_BX* RC_BY) k_raycast(RaycastParams p) {
-	const uint32_t x = blockIdx.x * RC_BX + threadIdx.x;
-	const uint32_t y = p.row0 + blockIdx.y * RC_BY + threadIdx.y;
+// CTA = 32x8 pixels as 8 warps of 8x4 pixels: neighbouring rays walk neighbouring voxels (L1 reuse of the taps)
+#define RCK_BX 32
+#define RCK_BY 4
+__global__ void __launch_bounds__(RCK_BX* RCK_BY) k_raycast(RaycastParams p) {
+	const uint32_t tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+	const uint32_t x = blockIdx.x * RCK_BX + (wid & 3) * 8 + (lane & 7);
+	const uint32_t y = p.row0 + blockIdx.y * RCK_BY + (wid >> 2) * 4 + (lane >> 3);
 	if (x >= p.w || y >= p.row1) return;
 	const size_t idx = (size_t) x + (size_t) y * p.w;
 	float hw;
