@@ -83,6 +83,7 @@ struct kfb_ctx {
 	unsigned int* d_bar;        // k_icp grid barrier: [0] arrivals, [1] generation, [2] converged
 	float* d_pose;              // k_icp: current pose [16]
 	int icp_grid;               // co-resident CTAs for the cooperative launch
+	unsigned long long* d_icp_prof;   // phase timers, only with KFB_ICP_PROFILE=1
 	float* h_out32_dev;
 	uint32_t seq;
 	unsigned long long* d_nupd; // NUPD_SLOTS per-integrate counters
@@ -269,6 +270,8 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	CK(cudaMalloc(&c->d_bar, 4 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_bar, 0, 4 * sizeof(unsigned int), c->stream));
 	CK(cudaMalloc(&c->d_pose, 16 * sizeof(float)));
+	c->d_icp_prof = nullptr;
+	if (getenv("KFB_ICP_PROFILE")) { CK(cudaMalloc(&c->d_icp_prof, 8 * sizeof(unsigned long long))); CK(cudaMemsetAsync(c->d_icp_prof, 0, 8 * sizeof(unsigned long long), c->stream)); }
 	{
 		int coop = 0, per_sm = 0, sms = 0;
 		CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
@@ -323,6 +326,13 @@ int kfb_destroy(kfb_ctx* c) {
 	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_floatDepth);
 	for (int l = 0; l < c->levels; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
 	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax); cudaFree(c->d_queue_ctr); if (c->d_queue) cudaFree(c->d_queue);
+	if (c->d_icp_prof) {
+		unsigned long long h[8];
+		if (cudaMemcpy(h, c->d_icp_prof, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[4])
+			fprintf(stderr, "kfb icp profile: %llu iterations; per iteration: last-CTA compute %.2f us, final reduce %.2f us, solve %.2f us, whole iteration (CTA 0) %.2f us\n",
+					h[4], h[0] * 1e-3 / h[4], h[1] * 1e-3 / h[4], h[2] * 1e-3 / h[4], h[3] * 1e-3 / h[4]);
+		cudaFree(c->d_icp_prof);
+	}
 	cudaFreeHost(c->h_out32); cudaFree(c->d_bar); cudaFree(c->d_pose);
 	if (c->d_input) cudaFree(c->d_input);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -559,7 +569,7 @@ int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracki
 			p.refV = c->d_vertex; p.refN = c->d_normal; p.rw = c->cw; p.rh = c->ch;
 			p.pose0 = toMat(c->pose); p.view = toMat(projectReference);
 			p.dist_threshold = c_dist_threshold; p.normal_threshold = c_normal_threshold; p.icp_threshold = icp_threshold;
-			p.partials = c->d_partials; p.bar = c->d_bar; p.pose_dev = c->d_pose;
+			p.partials = c->d_partials; p.bar = c->d_bar; p.pose_dev = c->d_pose; p.out32 = c->d_out32; p.prof = c->d_icp_prof;
 			p.out_host = c->h_out32_dev;
 			p.seq = ++c->seq;
 			p.status = (c->cfg.flags & KFB_FLAG_TRACK_STATUS) ? c->d_status : nullptr;

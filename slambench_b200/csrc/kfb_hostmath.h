@@ -141,7 +141,7 @@ KFB_HM int hm_solve6_chol(double* x6, const float* vals27) {
 		for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
 		if (!(s > 0)) return 0;
 		const double d = sqrt(s), inv = 1.0 / d;
-		L[j][j] = d;
+		L[j][j] = d; M[j][j] = inv;
 #pragma unroll
 		for (int i = j + 1; i < 6; ++i) {
 			double t = C[i][j];
@@ -154,14 +154,13 @@ KFB_HM int hm_solve6_chol(double* x6, const float* vals27) {
 	double trInv = 0;
 #pragma unroll
 	for (int j = 0; j < 6; ++j) {
-		M[j][j] = 1.0 / L[j][j];
-		trInv += M[j][j] * M[j][j];
+		trInv += M[j][j] * M[j][j];   // M[j][j] = 1 / L[j][j] from the factorisation
 #pragma unroll
 		for (int i = j + 1; i < 6; ++i) {
 			double t = 0;
 #pragma unroll
 			for (int k = j; k < i; ++k) t -= L[i][k] * M[k][j];
-			M[i][j] = t / L[i][i];
+			M[i][j] = t * M[i][i];
 			trInv += M[i][j] * M[i][j];
 		}
 	}

@@ -258,6 +258,81 @@ __device__ __forceinline__ void track_pixel(TrackAcc& a, const float* __restrict
 	}
 }
 
+// the same for U pixels at once, staged so that the U x (inN, inV) loads and then the U x (refN, refV) gathers are
+// all in flight together (the per-pixel chain input -> projection -> gather is latency-bound otherwise).
+// Invalid / out-of-image pixels gather from index 0 (in bounds) and discard the values: results are identical.
+template <int U>
+__device__ __forceinline__ void track_pixels(TrackAcc& a, const float* __restrict__ inV, const float* __restrict__ inN,
+		const float* __restrict__ refV, const float* __restrict__ refN, uint32_t w, uint32_t rw, uint32_t rh, const uint32_t (&pix)[U],
+		const bool (&on)[U], const Mat4& T, const Mat4& V, float dist_threshold, float normal_threshold, int8_t* status) {
+	float3 n[U], vin[U], pv[U], rn[U], rv[U];
+	int res[U];
+	size_t ridx[U];
+#pragma unroll
+	for (int u = 0; u < U; ++u) {
+		const size_t idx = on[u] ? (size_t) pix[u] : 0;
+		n[u] = ld3(inN, idx);
+		vin[u] = ld3(inV, idx);
+	}
+#pragma unroll
+	for (int u = 0; u < U; ++u) {
+		res[u] = 0;
+		ridx[u] = 0;
+		pv[u] = mat_point(T, vin[u]);
+		if (n[u].x == KFB_INVALID) res[u] = -1;
+		else {
+			const float3 pp = mat_point(V, pv[u]);
+			const float pixx = pp.x / pp.z + 0.5f, pixy = pp.y / pp.z + 0.5f;
+			if (pixx < 0 || pixx > (float) (rw - 1) || pixy < 0 || pixy > (float) (rh - 1)) res[u] = -2;
+			else ridx[u] = (size_t) (uint32_t) pixx + (size_t) (uint32_t) pixy * rw;   // (uint)NaN == 0, like x86-64
+		}
+	}
+#pragma unroll
+	for (int u = 0; u < U; ++u) {
+		rn[u] = ld3(refN, ridx[u]);
+		rv[u] = ld3(refV, ridx[u]);
+	}
+#pragma unroll
+	for (int u = 0; u < U; ++u) {
+		if (!on[u]) continue;
+		int result = res[u];
+		float err = 0.f;
+		float3 Ja = f3(0, 0, 0), Jb = f3(0, 0, 0);
+		if (result == 0) {
+			if (rn[u].x == KFB_INVALID) result = -3;
+			else {
+				const float3 diff = rv[u] - pv[u];
+				const float3 pn = mat_rotate(T, n[u]);
+				if (klength(diff) > dist_threshold) result = -4;
+				else if (kdot(pn, rn[u]) < normal_threshold) result = -5;
+				else {
+					result = 1;
+					err = kdot(rn[u], diff);
+					Ja = rn[u];
+					Jb = kcross(pv[u], rn[u]);
+				}
+			}
+		}
+		if (status) status[(size_t) (pix[u] % w) + (size_t) (pix[u] / w) * rw] = (int8_t) result;
+		if (result < 1) {
+			a.c29 += (result == -4);
+			a.c30 += (result == -5);
+			a.c31 += (result > -4);
+		} else {
+			const float J[6] = { Ja.x, Ja.y, Ja.z, Jb.x, Jb.y, Jb.z };
+			a.s[0] += err * err;
+#pragma unroll
+			for (int k = 0; k < 6; ++k) a.s[1 + k] += err * J[k];
+			int q = 7;
+#pragma unroll
+			for (int i = 0; i < 6; ++i)
+#pragma unroll
+				for (int j = i; j < 6; ++j) a.s[q++] += J[i] * J[j];
+			a.c28 += 1;
+		}
+	}
+}
+
 __global__ void __launch_bounds__(TR_THREADS) k_track_reduce(TrackParams p) {
 	__shared__ double sm[TR_THREADS / 32][32];
 	__shared__ bool is_last;
@@ -348,7 +423,9 @@ struct IcpParams {
 	Mat4 pose0, view;                       // pose at entry (:947), projectReference (:948)
 	float dist_threshold, normal_threshold, icp_threshold;
 	double* partials;                       // [gridDim.x][32]
-	unsigned int* bar;                      // [0] arrival counter, [1] generation, [2] converged flag of the last solve
+	unsigned int* bar;                      // [0] arrival counter, [1] generation, [2] converged flag of the last solve, [3] iterations
+	float* out32;                           // [32] device copy of the sums
+	unsigned long long* prof;               // optional phase timers (KFB_ICP_PROFILE): see k_icp
 	float* pose_dev;                        // [16] current pose (global; rewritten by the last CTA each iteration)
 	float* out_host;                        // mapped: [0..31] sums, [32] seq, [33] error, [48..63] pose, [64] iterations
 	uint32_t seq;
@@ -364,68 +441,103 @@ __device__ __forceinline__ void st_release_u32(unsigned int* p, unsigned int v) 
 	asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// one thread: updatePoseKernel (:759-775)
-__device__ __noinline__ int icp_solve(float* pose_dev, float* out_host, const float* red32, float icp_threshold) {
+__device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
+	unsigned int v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+// one thread: updatePoseKernel (:759-775) on the device copy of the pose
+__device__ __noinline__ int icp_solve(float* pose_dev, const float* red32, float icp_threshold) {
 	float pose[16];
 #pragma unroll
 	for (int i = 0; i < 16; ++i) pose[i] = pose_dev[i];
 	const int conv = hm_update_pose_fast(pose, red32, icp_threshold);
 #pragma unroll
-	for (int i = 0; i < 16; ++i) { pose_dev[i] = pose[i]; out_host[48 + i] = pose[i]; }
+	for (int i = 0; i < 16; ++i) pose_dev[i] = pose[i];
 	return conv;
+}
+
+__device__ __forceinline__ unsigned long long gtime_ns() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
 }
 
 __global__ void __launch_bounds__(TR_THREADS, 2) k_icp(IcpParams p) {
 	__shared__ double sm[TR_THREADS / 32][32];
+	__shared__ float xs[32][TR_THREADS];   // 32 KB: per-thread sums, transposed
 	__shared__ float red32[32];
 	__shared__ Mat4 Tsh;
-	__shared__ int flag_sh;   // bit 0: this CTA arrived last; after the barrier: converged / error
+	__shared__ int flag_sh;   // 1: this CTA arrived last; 2: barrier time-out
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const unsigned int gen0 = ld_acquire_u32(p.bar + 1);   // nobody advances it before every CTA has arrived once
-	unsigned int step = 0, iters = 0;
+	unsigned int step = 0;
 	const Mat4 V = p.view;
 
 	for (int level = p.levels - 1; level >= 0; --level) {
 		const uint32_t w = p.w[level], npx = p.w[level] * p.h[level];
 		for (int it = 0; it < p.iterations[level]; ++it) {
+			unsigned long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;
+			if (p.prof && threadIdx.x == 0) tp0 = gtime_ns();
 			if (threadIdx.x < 16) Tsh.m[threadIdx.x] = (step == 0) ? p.pose0.m[threadIdx.x] : __ldcg(p.pose_dev + threadIdx.x);
 			__syncthreads();
 			const Mat4 T = Tsh;
 			TrackAcc acc;
 			acc.clear();
-			for (uint32_t i = blockIdx.x * TR_THREADS + threadIdx.x; i < npx; i += gridDim.x * TR_THREADS)
-				track_pixel(acc, p.inV[level], p.inN[level], p.refV, p.refN, w, p.rw, p.rh, i % w, i / w, T, V, p.dist_threshold,
+			for (uint32_t i = blockIdx.x * TR_THREADS + threadIdx.x; i < npx; i += 2 * gridDim.x * TR_THREADS) {
+				const uint32_t pix[2] = { i, i + gridDim.x * TR_THREADS };
+				const bool on[2] = { true, pix[1] < npx };
+				track_pixels<2>(acc, p.inV[level], p.inN[level], p.refV, p.refN, w, p.rw, p.rh, pix, on, T, V, p.dist_threshold,
 						p.normal_threshold, p.status);
-			// warp -> CTA, fp64, fixed order
-#pragma unroll
-			for (int i = 0; i < 28; ++i) {
-				const double v = warp_sum((double) acc.s[i]);
-				if (lane == 0) sm[wid][i] = v;
 			}
-			{
-				const double v28 = warp_sum((double) acc.c28), v29 = warp_sum((double) acc.c29), v30 = warp_sum((double) acc.c30),
-						v31 = warp_sum((double) acc.c31);
-				if (lane == 0) { sm[wid][28] = v28; sm[wid][29] = v29; sm[wid][30] = v30; sm[wid][31] = v31; }
-			}
+			// thread -> CTA through shared memory, fp64, fixed order: value i of thread t sits at xs[i][t]; warp w
+			// sums values 4w..4w+3 (lane l adds threads l, l+32, .. in order, then a 5-step butterfly)
 			__syncthreads();
-			if (wid == 0) {
+#pragma unroll
+			for (int i = 0; i < 28; ++i) xs[i][threadIdx.x] = acc.s[i];
+			xs[28][threadIdx.x] = (float) acc.c28; xs[29][threadIdx.x] = (float) acc.c29;
+			xs[30][threadIdx.x] = (float) acc.c30; xs[31][threadIdx.x] = (float) acc.c31;
+			__syncthreads();
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				const int i = wid * 4 + q;
 				double v = 0;
 #pragma unroll
-				for (int k = 0; k < TR_THREADS / 32; ++k) v += sm[k][lane];
-				__stcg(p.partials + (size_t) blockIdx.x * 32 + lane, v);
-				__threadfence();
+				for (int k = 0; k < TR_THREADS / 32; ++k) v += (double) xs[i][lane + 32 * k];
+				v = warp_sum(v);
+				if (lane == 0) __stcg(p.partials + (size_t) blockIdx.x * 32 + i, v);
 			}
+			__threadfence();
 			__syncthreads();
-			++step; ++iters;
+			++step;
+			if (p.prof && threadIdx.x == 0) tp1 = gtime_ns();
 			if (threadIdx.x == 0) flag_sh = (atomicAdd(p.bar, 1u) == gridDim.x - 1) ? 1 : 0;
 			__syncthreads();
 			if (flag_sh) {
-				// last CTA: every partial row is visible (each writer fenced before its ticket)
+				// last CTA: every partial row is visible (each writer fenced before its ticket).  Warp w sums rows
+				// w, w+8, ... with four independent accumulators (loads overlap), always in the same order.
 				__threadfence();
-				double v = 0;
-				for (uint32_t b = wid; b < gridDim.x; b += TR_THREADS / 32) v += __ldcg(p.partials + (size_t) b * 32 + lane);
-				__syncthreads();
-				sm[wid][lane] = v;
+				double va[8];
+#pragma unroll
+				for (int j = 0; j < 8; ++j) va[j] = 0;
+				uint32_t b = wid;
+				const double* part = p.partials + lane;
+				for (; b + 56 < gridDim.x; b += 64) {
+					double a[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) a[j] = __ldcg(part + (size_t) (b + 8 * j) * 32);
+#pragma unroll
+					for (int j = 0; j < 8; ++j) va[j] += a[j];
+				}
+				{
+					double a[8];
+#pragma unroll
+					for (int j = 0; j < 8; ++j) a[j] = (b + 8 * j < gridDim.x) ? __ldcg(part + (size_t) (b + 8 * j) * 32) : 0.0;
+#pragma unroll
+					for (int j = 0; j < 8; ++j) va[j] += a[j];
+				}
+				sm[wid][lane] = ((va[0] + va[1]) + (va[2] + va[3])) + ((va[4] + va[5]) + (va[6] + va[7]));
 				__syncthreads();
 				if (wid == 0) {
 					double t = 0;
@@ -433,26 +545,33 @@ __global__ void __launch_bounds__(TR_THREADS, 2) k_icp(IcpParams p) {
 					for (int k = 0; k < TR_THREADS / 32; ++k) t += sm[k][lane];
 					const float r = (float) t;
 					red32[lane] = r;
-					p.out_host[lane] = r;
+					p.out32[lane] = r;            // device copy; mirrored to the host once, at the end
 					__syncwarp();
 					if (lane == 0) {
+						if (p.prof) tp2 = gtime_ns();
 						if (step == 1) {
 #pragma unroll
 							for (int i = 0; i < 16; ++i) p.pose_dev[i] = p.pose0.m[i];
 						}
-						const int c = icp_solve(p.pose_dev, p.out_host, red32, p.icp_threshold);
-						reinterpret_cast<volatile unsigned int*>(p.out_host)[64] = iters;
+						const int c = icp_solve(p.pose_dev, red32, p.icp_threshold);
+						if (p.prof) {   // last CTA: [0] own compute, [1] final reduce, [2] solve (ns, summed over iterations)
+							tp3 = gtime_ns();
+							atomicAdd(p.prof + 0, tp1 - tp0); atomicAdd(p.prof + 1, tp2 - tp1); atomicAdd(p.prof + 2, tp3 - tp2);
+							atomicAdd(p.prof + 4, 1ull);
+						}
 						p.bar[2] = (unsigned int) c;
+						p.bar[3] = step;                    // iterations executed so far
 						p.bar[0] = 0;                       // re-arm the arrival counter
-						__threadfence_system();             // pose + sums reach the host before anybody can publish `seq`
 						st_release_u32(p.bar + 1, gen0 + step);
 					}
 				}
 			} else if (threadIdx.x == 0) {
-				unsigned long long spins = 0;
-				while (ld_acquire_u32(p.bar + 1) != gen0 + step) {
-					if (++spins > (1ull << 22)) { flag_sh = 2; break; }   // ~1 s: a lost CTA must not hang the GPU
+				unsigned int spins = 0;
+				while (ld_relaxed_u32(p.bar + 1) != gen0 + step) {
+					__nanosleep(64);
+					if (++spins > (1u << 22)) { flag_sh = 2; break; }   // ~1 s: a lost CTA must not hang the GPU
 				}
+				__threadfence();   // acquire: the last CTA's pose / flags are visible below
 			}
 			__syncthreads();
 			if (flag_sh == 2) {   // barrier time-out (cannot happen under a cooperative launch): report and leave
@@ -460,13 +579,19 @@ __global__ void __launch_bounds__(TR_THREADS, 2) k_icp(IcpParams p) {
 				return;
 			}
 			const unsigned int converged = __ldcg(p.bar + 2);
+			if (p.prof && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(p.prof + 3, gtime_ns() - tp0);   // [3] whole iteration seen by CTA 0
 			__syncthreads();
 			if (converged) break;   // updatePoseKernel returned true: next level (:963-964)
 		}
 	}
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
+	// results to the host, once per frame: sums of the last iteration, final pose, iteration count, then the flag
+	if (blockIdx.x == 0 && wid == 0) {
+		p.out_host[lane] = __ldcg(p.out32 + lane);
+		if (lane < 16) p.out_host[48 + lane] = __ldcg(p.pose_dev + lane);
+		if (lane == 0) reinterpret_cast<volatile unsigned int*>(p.out_host)[64] = __ldcg(p.bar + 3);
+		__syncwarp();
 		__threadfence_system();
-		*reinterpret_cast<volatile unsigned int*>(p.out_host + 32) = p.seq;
+		if (lane == 0) *reinterpret_cast<volatile unsigned int*>(p.out_host + 32) = p.seq;
 	}
 }
 
@@ -762,7 +887,10 @@ __device__ __forceinline__ float vol_interp(const VolView& v, float3 pos) {  // 
 	const float spy = div_const(pos.y * (float) v.sy, v.dy, v.rdy, v.fastdiv) - 0.5f;
 	const float spz = div_const(pos.z * (float) v.sz, v.dz, v.rdz, v.fastdiv) - 0.5f;
 	const float flx = floorf(spx), fly = floorf(spy), flz = floorf(spz);
-	const int bx = (int) flx, by = (int) fly, bz = (int) flz;
+	// base is in [-1, N-1] for every position the reference samples (inside the volume box); clamping the base itself
+	// changes nothing there and keeps the taps in bounds for any other position (NaN pose, renderVolume's 2x far plane)
+	const int bx = kmini(kmaxi((int) flx, -1), (int) v.sx - 1), by = kmini(kmaxi((int) fly, -1), (int) v.sy - 1),
+			bz = kmini(kmaxi((int) flz, -1), (int) v.sz - 1);
 	const float fx = spx - flx, fy = spy - fly, fz = spz - flz;
 	const int lx = kmaxi(bx, 0), ly = kmaxi(by, 0), lz = kmaxi(bz, 0);
 	const int ux = kmini(bx + 1, (int) v.sx - 1), uy = kmini(by + 1, (int) v.sy - 1), uz = kmini(bz + 1, (int) v.sz - 1);
