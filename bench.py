@@ -335,6 +335,84 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+def sharded_arm(args, rank: int, world: int, local_rank: int):
+    """ONE sequence, the volume cut into z-slabs over the ranks (BASELINE configs[3], [4]): integrate local, raycast
+    over NVLink peer slabs + NCCL all-gather, ICP replicated or all-reduced.  Strong scaling: the work is fixed."""
+    import torch
+    import torch.distributed as dist
+
+    from slambench_b200 import sharded, synth
+
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    K = np.array(synth.K_DEFAULT, np.float32)
+    T0 = (np.array(synth.INIT_POS_FACTOR, np.float32) * np.float32(VOLUME_DIM)).astype(np.float32)
+    n = args.warmup + args.steps
+    depth_np, gt = synth.make_sequence(n, long_run=False if n <= 400 else None)
+    host = torch.from_numpy(depth_np).pin_memory()
+    depth_np = host.numpy()
+    with sharded.ShardedKfusion((W_IMG, H_IMG), args.volume, VOLUME_DIM, T0, PYRAMID, rank=rank, world=world, device=local_rank,
+                                icp_mode=args.icp_mode) as s:
+        g = s.local
+        stream = g.torch_stream(torch)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+        def frame(f):
+            s.preprocessing(depth_np[f])
+            tr = s.tracking(K, ICP_THRESHOLD, 1, f)
+            s.integration(K, 1, MU, f)
+            s.raycasting(K, MU, f)
+            return tr
+
+        for f in range(args.warmup):
+            frame(f)
+        s.synchroniseDevices()
+        g.enable_timing(4)
+        g.reset_stats()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev0.record(stream)
+        tracked = 0
+        for f in range(args.warmup, n):
+            tracked += frame(f)
+        ev1.record(stream)
+        s.synchroniseDevices()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        dist.barrier()
+        ms = max(ev0.elapsed_time(ev1), wall)
+        st = g.stats()
+        t = torch.tensor([ms, float(st["voxels_updated_total"]), st["ms_integrate"]], dtype=torch.float64, device=f"cuda:{local_rank}")
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        err = float(np.abs(s.getPose()[:3, 3] - gt[n - 1][:3, 3]).max())
+        if rank == 0:
+            peak, peak_src = peaks()
+            ms_all = float(tmax[0])
+            n_int = max(1, int(st["frames_integrated"]))
+            alg = (8.0 * float(tsum[1]) + 4.0 * P_PIX * n_int * world) / n_int          # all slabs together
+            t_int = float(tmax[2]) / n_int * 1e-3                                          # slowest slab
+            line = {
+                "metric": METRIC, "value": args.steps / (ms_all * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": workload_name(args.volume), "volume": args.volume, "frames": n,
+                           "parallelism": f"z-slab x{world}: integrate local, raycast via NVLink peer slabs + NCCL all-gather, ICP {args.icp_mode}",
+                           "tracked_frames": int(tracked), "final_pose_err_m": err},
+                "e2e": {"value": args.steps / (ms_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W_IMG * H_IMG * 2,
+                        "d2h_bytes_per_step": st["d2h_bytes"] / args.steps},
+                "gpu_launches": int(st["kernel_launches"]) * world,
+                "roofline": {"bound": "hbm", "kernel": "k_integrate_run", "achieved": alg / t_int / 1e9, "peak": peak * world, "unit": "GB/s",
+                             "frac": alg / t_int / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src + f" x{world}",
+                             "us_per_launch": t_int * 1e6},
+            }
+            print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -345,6 +423,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true", help="skip the extra per-stage timing pass")
+    ap.add_argument("--mode", default="sequences", choices=["sequences", "sharded"],
+                    help="N > 1: one independent sequence per GPU (weak scaling, default) or ONE sequence on a z-slab sharded volume (strong)")
+    ap.add_argument("--icp-mode", default="replicated", choices=["replicated", "allreduce"])
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes/launch of k_integrate from the ncu capture in profiles/")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -357,6 +438,9 @@ def main():
         return
     if world != args.gpus and world == 1 and args.gpus > 1:
         raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one process per GPU)")
+    if args.mode == "sharded" and world > 1:
+        sharded_arm(args, rank, world, local_rank)
+        return
     b200_arm(args, rank, world, local_rank)
 
 

@@ -73,7 +73,8 @@ enum kfb_buffer {
 	KFB_BUF_RAYCASTPOSE = 9,  /* float[16] (host)                                         `raycastPose`      */
 	KFB_BUF_OLDPOSE = 10,     /* float[16] (host)                                         `oldPose`          */
 	KFB_BUF_GAUSSIAN = 11,    /* float[5]                                                 `gaussian`         */
-	KFB_BUF_INPUTDEPTH = 12   /* uint16[in_w*in_h] device copy of the last sensor frame                      */
+	KFB_BUF_INPUTDEPTH = 12,  /* uint16[in_w*in_h] device copy of the last sensor frame                      */
+	KFB_BUF_REDUCTION_DEV = 13 /* float[32] DEVICE copy of the last track+reduce result (multi-GPU all-reduce operand) */
 };
 
 int kfb_abi_version(void);
@@ -164,9 +165,10 @@ int kfb_stream(kfb_ctx* ctx, void** stream);
 int kfb_slab_ipc_handle(kfb_ctx* ctx, uint8_t handle64[64]);
 /* import the peers' slabs: handles[r] / z_begin[r] for r in [0, world); own rank's entry is ignored */
 int kfb_slab_import(kfb_ctx* ctx, int rank, int world, const uint8_t* handles64, const uint32_t* z_begin);
-/* attach an NCCL communicator (ncclComm_t as void*, created by the host harness) for the ICP all-reduce and
- * the raycast all-gather */
-int kfb_attach_nccl(kfb_ctx* ctx, void* nccl_comm, int rank, int world);
+/* rows [row0, row1) of the computation image this context is responsible for in kfb_raycast / kfb_k_raycast and in
+ * the stage-level kfb_k_track_reduce (level l uses [row0 >> l, row1 >> l)); (0, 0) = the whole image.  The host
+ * harness all-gathers the raycast bands and all-reduces the 32 partial sums (KFB_BUF_REDUCTION_DEV) over NCCL. */
+int kfb_set_pixel_rows(kfb_ctx* ctx, uint32_t row0, uint32_t row1);
 
 #ifdef __cplusplus
 }

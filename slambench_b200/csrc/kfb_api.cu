@@ -101,7 +101,7 @@ struct kfb_ctx {
 	int rank, world;
 	VolView view_all;           // slab table for raycast
 	void* peer_ptrs[KFB_MAX_SLABS];
-	void* nccl_comm;
+	uint32_t band0, band1;      // pixel rows handled by this context (multi-GPU); whole image by default
 	// registered host pointers (benchmark.cpp reuses one malloc'd frame buffer)
 	const void* reg_ptr[4]; size_t reg_bytes[4]; int n_reg;
 	// stats
@@ -233,7 +233,7 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	if (c->z1 > cfg->volume_res[2] || c->z0 >= c->z1) { delete c; return set_err(KFB_E_ARG, "bad z-slab [%u,%u)", cfg->slab_z0, cfg->slab_z1); }
 	c->slab_voxels = (size_t) cfg->volume_res[0] * cfg->volume_res[1] * (c->z1 - c->z0);
 	c->timing = 0;
-	c->rank = 0; c->world = 1; c->nccl_comm = nullptr;
+	c->rank = 0; c->world = 1; c->band0 = 0; c->band1 = cfg->compute_h;
 	c->n_reg = 0;
 	c->d_input = nullptr; c->input_bytes = 0; c->h_stage = nullptr; c->stage_bytes = 0;
 	c->d_render = nullptr; c->render_bytes = 0;
@@ -493,7 +493,8 @@ static int launch_track(kfb_ctx* c, int level, const float* T, const float* V, f
 	p.inV = c->d_inV[level]; p.inN = c->d_inN[level];
 	p.refV = c->d_vertex; p.refN = c->d_normal;
 	p.w = c->lw[level]; p.h = c->lh[level]; p.rw = c->cw; p.rh = c->ch;
-	p.row0 = 0; p.row1 = p.h;
+	p.row0 = c->band0 >> level; p.row1 = c->band1 >> level;   // whole level unless kfb_set_pixel_rows narrowed it
+	if (c->band1 == c->ch) p.row1 = p.h;
 	p.Ttrack = toMat(T); p.view = toMat(V);
 	p.pose_dev = nullptr; p.view_dev = nullptr;
 	p.dist_threshold = dist; p.normal_threshold = nthr;
@@ -678,7 +679,7 @@ static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP
 	p.vol = c->view_all;
 	p.vertex = c->d_vertex; p.normal = c->d_normal;
 	p.w = c->cw; p.h = c->ch;
-	p.row0 = 0; p.row1 = c->ch;
+	p.row0 = c->band0; p.row1 = c->band1;
 	p.view = toMat(view);
 	p.nearPlane = nearP; p.farPlane = farP; p.step = step; p.largestep = largestep;
 	dim3 block(RCK_BX * RCK_BY), grid((p.w + RCK_BX - 1) / RCK_BX, (p.row1 - p.row0 + RCK_BY - 1) / RCK_BY);
@@ -829,6 +830,7 @@ static int resolve_buffer(kfb_ctx* c, int which, int level, void** ptr, size_t* 
 	case KFB_BUF_OLDPOSE: *ptr = c->oldPose; *bytes = 64; *host = true; break;
 	case KFB_BUF_GAUSSIAN: *ptr = c->gaussian; *bytes = 20; *host = true; break;
 	case KFB_BUF_INPUTDEPTH: *ptr = c->d_input; *bytes = c->input_bytes; break;
+	case KFB_BUF_REDUCTION_DEV: *ptr = c->d_out32; *bytes = 32 * 4; break;
 	default: return set_err(KFB_E_ARG, "unknown buffer %d", which);
 	}
 	return 0;
@@ -928,8 +930,10 @@ int kfb_slab_import(kfb_ctx* c, int rank, int world, const uint8_t* handles64, c
 	if (z_begin[rank] != c->z0) return set_err(KFB_E_ARG, "z_begin[%d]=%u does not match this context's slab start %u", rank, z_begin[rank], c->z0);
 	return 0;
 }
-int kfb_attach_nccl(kfb_ctx* c, void* comm, int rank, int world) {
-	c->nccl_comm = comm; c->rank = rank; c->world = world;
+int kfb_set_pixel_rows(kfb_ctx* c, uint32_t row0, uint32_t row1) {
+	if (row0 == 0 && row1 == 0) row1 = c->ch;
+	if (row1 > c->ch || row0 >= row1) return set_err(KFB_E_ARG, "bad pixel rows [%u,%u) for a %u-row image", row0, row1, c->ch);
+	c->band0 = row0; c->band1 = row1;
 	return 0;
 }
 

@@ -23,7 +23,7 @@ FLAG_NO_GRAPHS = 0x4
 FLAG_INTEGRATE_NO_CULL = 0x8
 
 (BUF_VOLUME, BUF_VERTEX, BUF_NORMAL, BUF_FLOATDEPTH, BUF_SCALEDDEPTH, BUF_INVERTEX, BUF_INNORMAL,
- BUF_REDUCTION, BUF_TRACKSTATUS, BUF_RAYCASTPOSE, BUF_OLDPOSE, BUF_GAUSSIAN, BUF_INPUTDEPTH) = range(13)
+ BUF_REDUCTION, BUF_TRACKSTATUS, BUF_RAYCASTPOSE, BUF_OLDPOSE, BUF_GAUSSIAN, BUF_INPUTDEPTH, BUF_REDUCTION_DEV) = range(14)
 
 # constant_parameters.h:15-23
 E_DELTA, RADIUS, DIST_THRESHOLD, NORMAL_THRESHOLD, TRACK_THRESHOLD = 0.1, 2, 0.1, 0.8, 0.15
@@ -303,6 +303,7 @@ class Kfusion:
             BUF_INVERTEX: ((lh, lw, 3), np.float32), BUF_INNORMAL: ((lh, lw, 3), np.float32),
             BUF_REDUCTION: ((32,), np.float32), BUF_TRACKSTATUS: ((h, w), np.int8),
             BUF_RAYCASTPOSE: ((4, 4), np.float32), BUF_OLDPOSE: ((4, 4), np.float32), BUF_GAUSSIAN: ((5,), np.float32),
+            BUF_REDUCTION_DEV: ((32,), np.float32),
         }[which]
 
     def read(self, which: int, level: int = 0) -> np.ndarray:
@@ -329,6 +330,10 @@ class Kfusion:
         self._check(self.lib.kfb_stream(self._h, C.byref(s)))
         return s.value or 0
 
+    def torch_stream(self, torch):
+        """This context's CUDA stream as a torch ExternalStream (collectives of the sharded mode are enqueued on it)."""
+        return torch.cuda.ExternalStream(self.stream(), device=self.cfg.device)
+
     def enable_timing(self, on=True):
         """`on`: True/False for all stages, or a bitmask (1 preprocess, 2 track, 4 integrate, 8 raycast)."""
         mask = (15 if on else 0) if isinstance(on, bool) else int(on)
@@ -343,6 +348,9 @@ class Kfusion:
         return {f: getattr(st, f) for f, _ in KfbStats._fields_}
 
     # ---------------------------------------------------------------- multi-GPU
+    def set_pixel_rows(self, row0: int, row1: int):
+        self._check(self.lib.kfb_set_pixel_rows(self._h, C.c_uint32(row0), C.c_uint32(row1)))
+
     def slab_ipc_handle(self) -> bytes:
         buf = (C.c_uint8 * 64)()
         self._check(self.lib.kfb_slab_ipc_handle(self._h, buf))

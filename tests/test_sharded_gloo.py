@@ -1,0 +1,205 @@
+"""Host-side logic of the z-slab sharded mode (slambench_b200/sharded.py) on the CPU: world_size 2,
+`gloo` backend, a numpy stand-in for the per-GPU context.  Checks the partitioning, the band
+all-gather, the stream-ordered barrier calls, the all-reduced ICP iteration loop (with the product's
+real host pose algebra from libkfb200.so) and the slab gather."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from slambench_b200 import kfusion as kf
+from slambench_b200 import sharded
+
+W, H, N = 64, 48, 16
+
+
+def test_partitions():
+    assert sharded.slab_bounds(1024, 8) == [(i * 128, (i + 1) * 128) for i in range(8)]
+    s = sharded.slab_bounds(10, 4)
+    assert s == [(0, 3), (3, 6), (6, 8), (8, 10)] and s[-1][1] == 10
+    assert sharded.row_bands(480, 8)[3] == (180, 240)
+    with pytest.raises(ValueError):
+        sharded.row_bands(480, 7)
+    with pytest.raises(ValueError):
+        sharded.slab_bounds(3, 4)
+
+
+def synthetic_track_data(level):
+    """Deterministic per-pixel (error, J) for a level: the 'image' every rank reduces a band of."""
+    w, h = W >> level, H >> level
+    rng = np.random.default_rng(100 + level)
+    J = rng.normal(size=(h, w, 6)).astype(np.float32)
+    e = (rng.normal(size=(h, w)) * 1e-3).astype(np.float32)
+    return e, J
+
+
+def reduce_rows(level, r0, r1):
+    e, J = synthetic_track_data(level)
+    e, J = e[r0:r1].reshape(-1).astype(np.float64), J[r0:r1].reshape(-1, 6).astype(np.float64)
+    out = np.zeros(32)
+    out[0] = (e * e).sum()
+    out[1:7] = J.T @ e
+    out[7:28] = (J.T @ J)[np.triu_indices(6)]
+    out[28] = e.size
+    return out.astype(np.float32)
+
+
+class FakeLocal:
+    """numpy/torch-CPU stand-in with the subset of `Kfusion` that ShardedKfusion drives."""
+
+    def __init__(self, device, slab, flags):
+        self.slab, self.rows = slab, None
+        self.lib = kf.load_library()
+        self.t = {kf.BUF_VERTEX: torch.zeros(H, W, 3), kf.BUF_NORMAL: torch.zeros(H, W, 3), kf.BUF_REDUCTION_DEV: torch.zeros(32)}
+        self.pose = np.eye(4, dtype=np.float32)
+        self.host = {}
+        self.calls = []
+
+    def slab_ipc_handle(self):
+        return bytes([self.slab[0] % 251]) * 64
+
+    def slab_import(self, rank, world, handles, z_begin):
+        assert len(handles) == world and all(len(h) == 64 for h in handles)
+        assert handles[rank] == self.slab_ipc_handle() and z_begin[rank] == self.slab[0]
+        self.rank = rank
+
+    def set_pixel_rows(self, r0, r1):
+        self.rows = (r0, r1)
+
+    def tensor(self, which):
+        return self.t[which]
+
+    def preprocessing(self, d, size=None):
+        return True
+
+    def pyramidKernels(self, k):
+        self.calls.append("pyramid")
+
+    def getPose(self):
+        return self.pose.copy()
+
+    def setPose(self, p):
+        self.pose = np.array(p, np.float32)
+
+    def read(self, which):
+        return np.eye(4, dtype=np.float32)
+
+    def write(self, which, data):
+        self.host[which] = np.array(data)
+
+    def cameraMatrix(self, k):
+        return np.eye(4, dtype=np.float32)
+
+    def inverse(self, m):
+        return np.linalg.inv(m).astype(np.float32)
+
+    def matmul(self, a, b):
+        return (a @ b).astype(np.float32)
+
+    def trackReduceKernel(self, level, pose, view):
+        r0, r1 = self.rows[0] >> level, self.rows[1] >> level
+        self.t[kf.BUF_REDUCTION_DEV].copy_(torch.from_numpy(reduce_rows(level, r0, r1)))
+
+    def updatePoseKernel(self, pose, red, thr):
+        p = np.ascontiguousarray(pose, np.float32).reshape(16).copy()
+        conv = C.c_int(0)
+        self.lib.kfb_k_update_pose(p.ctypes.data_as(C.c_void_p), np.ascontiguousarray(red, np.float32).ctypes.data_as(C.c_void_p), C.c_float(thr), C.byref(conv))
+        return p.reshape(4, 4), bool(conv.value)
+
+    def checkPoseKernel(self, pose, old, red, size):
+        p = np.ascontiguousarray(pose, np.float32).reshape(16).copy()
+        ok = C.c_int(0)
+        self.lib.kfb_k_check_pose(p.ctypes.data_as(C.c_void_p), np.ascontiguousarray(old, np.float32).ctypes.data_as(C.c_void_p),
+                                  np.ascontiguousarray(red, np.float32).ctypes.data_as(C.c_void_p), C.c_uint32(size[0]), C.c_uint32(size[1]), C.c_float(0.15), C.byref(ok))
+        return p.reshape(4, 4), bool(ok.value)
+
+    def integration(self, k, rate, mu, frame):
+        self.calls.append("integrate")
+        return True
+
+    def raycasting(self, k, mu, frame):
+        r0, r1 = self.rows
+        rows = torch.arange(r0, r1, dtype=torch.float32)[:, None, None]
+        self.t[kf.BUF_VERTEX][r0:r1] = rows + 1000 * (self.rank + 1)
+        self.t[kf.BUF_NORMAL][r0:r1] = -rows - 1000 * (self.rank + 1)
+        return False
+
+    def read_volume(self):
+        return np.full((self.slab[1] - self.slab[0], 2, 2, 2), self.rank, np.int16)
+
+    def close(self):
+        pass
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        holder = {}
+
+        def factory(**kw):
+            holder["l"] = FakeLocal(**kw)
+            return holder["l"]
+
+        s = sharded.ShardedKfusion((W, H), N, 4.8, np.zeros(3, np.float32), (3, 2, 2), rank=rank, world=world, icp_mode="allreduce",
+                                   dist=dist, local_factory=factory)
+        loc = holder["l"]
+        assert loc.slab == sharded.slab_bounds(N, world)[rank] and loc.rows == sharded.row_bands(H, world)[rank]
+        # raycast bands are all-gathered: every rank ends with the full maps
+        s.raycasting(None, 0.1, frame=5)
+        want = np.zeros((H, W, 3), np.float32)
+        for r, (r0, r1) in enumerate(sharded.row_bands(H, world)):
+            want[r0:r1] = np.arange(r0, r1, dtype=np.float32)[:, None, None] + 1000 * (r + 1)
+        assert np.array_equal(loc.t[kf.BUF_VERTEX].numpy(), want) and np.array_equal(loc.t[kf.BUF_NORMAL].numpy(), -want)
+        # frames <= 2: no raycast yet, no collective (cpp/kernels.cpp:977)
+        loc.t[kf.BUF_VERTEX].zero_()
+        s.raycasting(None, 0.1, frame=2)
+        assert float(loc.t[kf.BUF_VERTEX][sharded.row_bands(H, world)[1 - rank][0]].abs().sum()) == 0
+        # all-reduced ICP loop == the same loop on the whole image
+        tracked = s.tracking(np.zeros(4, np.float32), 1e-5, 1, frame=7)
+        pose = s.getPose()
+        ref_pose = np.eye(4, dtype=np.float32)
+        last = None
+        for level in (2, 1, 0):
+            for _ in range((3, 2, 2)[level]):
+                parts = [reduce_rows(level, b0 >> level, b1 >> level) for b0, b1 in sharded.row_bands(H, world)]
+                last = parts[0] + parts[1]
+                ref_pose, conv = loc.updatePoseKernel(ref_pose, last, 1e-5)
+                if conv:
+                    break
+        assert np.array_equal(pose, ref_pose), "pose after the all-reduced iterations"
+        assert np.array_equal(loc.host[kf.BUF_REDUCTION], last)
+        assert s.tracking(np.zeros(4, np.float32), 1e-5, 2, frame=7) is False       # frame % tracking_rate gate
+        assert s.integration(None, 1, 0.1, 7) is True
+        q.put((rank, pose.copy(), bool(tracked)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_sharded_orchestration_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    res.sort(key=lambda t: t[0])
+    assert np.array_equal(res[0][1], res[1][1]), "every rank must hold the same pose"
+    assert res[0][2] == res[1][2]
