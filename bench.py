@@ -20,7 +20,8 @@ SURVEY §8a a18), so every timed frame is tracked + integrated + raycast.
             built, the plain-C restatement, timed on this box's host cores on a bounded sample
 
 N > 1: one process per GPU, one independent sequence per GPU (BASELINE configs[2]), no data-path
-collective; value = sum of frames / max-over-ranks time ("weak" scaling).
+collective; value = sum of frames / max-over-ranks time ("weak" scaling).  `--mode sharded` instead
+runs ONE sequence on a volume cut into z-slabs over the ranks (configs[3], [4]; "strong" scaling).
 """
 from __future__ import annotations
 
@@ -73,54 +74,56 @@ def peaks():
 
 # ---------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled from a
+    background thread every ~2 ms (the timed region of the default run is only ~50 ms, too short for
+    `nvidia-smi -lms`)."""
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
-        self.proc = None
-        self.path = f"/tmp/kfb_clocks_{os.getpid()}.csv"
+        self.samples, self.bits = [], 0
+        self.max_mhz = None
+        self._stop = False
+        self._thread = None
+        try:
+            import pynvml  # noqa: PLC0415
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _poll(self):
+        nv = self.nv
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
-        try:
-            self.f = open(self.path, "w")
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                                          "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+        if self.nv is None:
+            return
+        import threading  # noqa: PLC0415
+
+        self._thread = threading.Thread(target=self._poll, daemon=True)
+        self._thread.start()
 
     def stop(self) -> dict:
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self._thread is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        self.f.close()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                c = [x.strip() for x in line.split(",")]
-                if len(c) < 9:
-                    continue
-                try:
-                    sm.append(float(c[1]))
-                    mx.append(float(c[2]))
-                except ValueError:
-                    continue
-                for nm, v in zip(names, c[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), samples=len(sm))
-        out["reasons"] = sorted(reasons)
+        self._stop = True
+        self._thread.join(timeout=2)
+        if self.samples:
+            out.update(sm_mhz=statistics.median(self.samples), samples=len(self.samples))
+        out["reasons"] = sorted(n for b, n in self.REASONS.items() if self.bits & b)
         return out
 
 

@@ -617,7 +617,7 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	// pass 1 cuts every warp-column's visited interval into pieces of `zchunk` slices; pass 2 is persistent
 	// short pieces keep every warp's serial chain short (measured: 256^3 best at 16-32, 512^3 at 64)
 	{
-		uint32_t zc = (c->z1 - c->z0) / 8;
+		uint32_t zc = ((c->z1 - c->z0) / 8) & ~7u;   // a multiple of INT_U so a warp can continue into the next piece
 		zc = zc < 16 ? 16 : (zc > 64 ? 64 : zc);
 		p.zchunk = c->int_zchunk ? c->int_zchunk : zc;
 	}
@@ -627,13 +627,16 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	p.queue_next = c->d_queue_ctr + 2 * (qslot ^ 1);
 	{
 		const uint32_t nz = c->z1 - c->z0;
-		const size_t need = (size_t) ((p.sx + 31) / 32) * p.sy * ((nz + p.zchunk - 1) / p.zchunk + 1);
+		(void) nz;
+		const size_t need = (size_t) ((p.sx + 31) / 32) * p.sy;   // one entry per warp-column
 		if (need > c->queue_cap) {
 			if (c->d_queue) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(c->d_queue)); }
-			CK(cudaMalloc(&c->d_queue, need * sizeof(uint2)));
+			CK(cudaMalloc(&c->d_queue, need * (sizeof(uint2) + sizeof(unsigned int))));
 			c->queue_cap = need;
 			p.queue = c->d_queue;
 		}
+		p.piece_ctr = reinterpret_cast<unsigned int*>(c->d_queue + c->queue_cap);
+		if (p.zchunk % INT_U != 0 || p.zchunk == 0) return set_err(KFB_E_ARG, "integrate piece length must be a positive multiple of %d", INT_U);
 	}
 	dim3 block(32, 8), grid((p.sx + 31) / 32, (p.sy + 7) / 8);
 	k_integrate_plan<<<grid, block, 0, c->stream>>>(p);

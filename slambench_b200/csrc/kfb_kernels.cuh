@@ -631,7 +631,8 @@ struct IntegrateParams {
 	const float* dmax;         // optional: max of the depth image (device scalar); nullptr = unknown
 	int cull;                  // 0 = visit every voxel (debug / A-B), 1 = interval + fast tests
 	unsigned long long* n_upd;
-	uint2* queue;              // work list: pieces of warp-column intervals
+	uint2* queue;              // work list: warp-columns with a non-empty visited interval
+	unsigned int* piece_ctr;   // per work-list entry: next unclaimed piece
 	unsigned int* queue_count; // [0] items appended by the plan pass, [1] next item (this frame's slot)
 	unsigned int* queue_head;
 	unsigned int* queue_next;  // the other slot's two counters, zeroed by the plan pass for the next frame
@@ -698,8 +699,8 @@ __device__ __forceinline__ IntColumn int_column(const IntegrateParams& p, uint32
 	return c;
 }
 
-// Pass 1: one warp per 32 x-adjacent columns: conservative interval, cut into pieces of `zchunk` slices,
-// appended to the work list.  item = { xtile | y << 16, z_start | len << 16 }.
+// Pass 1: one warp per 32 x-adjacent columns: conservative interval, appended to the work list.
+// entry = { xtile | y << 16, za | zb << 16 } plus a zeroed piece counter.
 __global__ void __launch_bounds__(256) k_integrate_plan(IntegrateParams p) {
 	const uint32_t x = blockIdx.x * 32 + threadIdx.x;
 	const uint32_t y = blockIdx.y * blockDim.y + threadIdx.y;   // warp-uniform
@@ -740,18 +741,19 @@ __global__ void __launch_bounds__(256) k_integrate_plan(IntegrateParams p) {
 	za = __reduce_min_sync(0xffffffffu, za);
 	zb = __reduce_max_sync(0xffffffffu, zb);
 	if (za >= zb) return;
-	const uint32_t pieces = ((uint32_t) (zb - za) + p.zchunk - 1) / p.zchunk;
-	uint32_t base = 0;
-	if (threadIdx.x == 0) base = atomicAdd(p.queue_count, pieces);
-	base = __shfl_sync(0xffffffffu, base, 0);
-	for (uint32_t i = threadIdx.x; i < pieces; i += 32) {
-		const uint32_t z0 = (uint32_t) za + i * p.zchunk;
-		const uint32_t len = min(p.zchunk, (uint32_t) zb - z0);
-		p.queue[base + i] = make_uint2(blockIdx.x | (y << 16), z0 | (len << 16));
+	if (threadIdx.x == 0) {
+		const uint32_t e = atomicAdd(p.queue_count, 1u);
+		p.queue[e] = make_uint2(blockIdx.x | (y << 16), (uint32_t) za | ((uint32_t) zb << 16));
+		p.piece_ctr[e] = 0u;
 	}
 }
 
-// Pass 2: persistent warps pull pieces from the work list (dynamic balance: no empty warps, no tail).
+// Pass 2: persistent warps.  A warp takes a warp-column from the list and sweeps it piece by piece (`zchunk`
+// slices, claimed one at a time from the column's counter), so the reference's additions are replayed only once
+// per column; warps that run out of fresh columns lap around the list and claim pieces of columns still in
+// progress (they replay the additions up to their piece), which removes the tail.  Every piece is processed
+// exactly once.
+#define INT_LAPS 4
 __global__ void __launch_bounds__(256, 4) k_integrate_run(IntegrateParams p) {
 	const uint32_t lane = threadIdx.x & 31;
 	const float dwm1 = (float) (p.dw - 1), dhm1 = (float) (p.dh - 1);
@@ -764,24 +766,40 @@ __global__ void __launch_bounds__(256, 4) k_integrate_run(IntegrateParams p) {
 	const uint32_t dw = p.dw;
 	const size_t plane = (size_t) p.sx * p.sy;
 	const unsigned int count = *p.queue_count;
+	const unsigned int visits = count * INT_LAPS;
 	unsigned int updated = 0;
 
 	for (;;) {
 		unsigned int it = 0;
 		if (lane == 0) it = atomicAdd(p.queue_head, 1u);
 		it = __shfl_sync(0xffffffffu, it, 0);
-		if (it >= count) break;
-		const uint2 item = __ldcg(p.queue + it);
+		if (it >= visits) break;
+		const unsigned int e = it % count;
+		const uint2 item = __ldcg(p.queue + e);
 		const uint32_t x = (item.x & 0xffffu) * 32 + lane, y = item.x >> 16;
-		const int za = (int) (item.y & 0xffffu), zb = za + (int) (item.y >> 16);
+		const int col_za = (int) (item.y & 0xffffu), col_zb = (int) (item.y >> 16);
+		const unsigned int npieces = ((unsigned int) (col_zb - col_za) + p.zchunk - 1) / p.zchunk;
 		const bool valid = x < p.sx;
-		const IntColumn c = int_column(p, x, y);
-		// running values, packed in pairs: (pos.x, pos.y) (pos.z, cam.x) (cam.y, cam.z)
-		F2 A = f2_make(c.pos0.x, c.pos0.y), B = f2_make(c.pos0.z, c.cam0.x), C = f2_make(c.cam0.y, c.cam0.z);
-		const F2 dA = f2_make(c.delta.x, c.delta.y), dB = f2_make(c.delta.z, c.cameraDelta.x), dC = f2_make(c.cameraDelta.y, c.cameraDelta.z);
-		// replay the reference's additions up to the first visited slice
+		F2 A, B, C, dA, dB, dC;
+		int zstate = -1;   // slice the running values correspond to; -1 = not computed yet
+	  for (;;) {
+		unsigned int pc = 0;
+		if (lane == 0) pc = atomicAdd(p.piece_ctr + e, 1u);
+		pc = __shfl_sync(0xffffffffu, pc, 0);
+		if (pc >= npieces) break;
+		const int za = col_za + (int) (pc * p.zchunk), zb = min(col_zb, za + (int) p.zchunk);
+		if (zstate < 0 || zstate > za) {
+			const IntColumn c = int_column(p, x, y);
+			// running values, packed in pairs: (pos.x, pos.y) (pos.z, cam.x) (cam.y, cam.z)
+			A = f2_make(c.pos0.x, c.pos0.y); B = f2_make(c.pos0.z, c.cam0.x); C = f2_make(c.cam0.y, c.cam0.z);
+			dA = f2_make(c.delta.x, c.delta.y); dB = f2_make(c.delta.z, c.cameraDelta.x); dC = f2_make(c.cameraDelta.y, c.cameraDelta.z);
+			zstate = 0;
+		}
+		// replay the reference's additions up to the first slice of the piece (nothing to do when the warp
+		// continues from the previous piece of the same column)
 #pragma unroll 8
-		for (int z = 0; z < za; ++z) { A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC); }
+		for (int z = zstate; z < za; ++z) { A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC); }
+		zstate = za + (int) (((unsigned int) (zb - za) + INT_U - 1) / INT_U * INT_U);   // the batches below advance in units of INT_U
 		short2* col = p.vol + (size_t) x + (size_t) y * p.sx + (size_t) ((uint32_t) za - p.z_begin) * plane;
 		// INT_U consecutive slices per batch: all decisions first, straight-line (depth gathers hit L1/L2), then
 		// all voxel loads back to back (INT_U independent 128-byte requests in flight per warp: the
@@ -826,6 +844,7 @@ __global__ void __launch_bounds__(256, 4) k_integrate_run(IntegrateParams p) {
 					++updated;
 				}
 		}
+	  }
 	}
 	// exact N_upd: one atomic per warp
 	updated = __reduce_add_sync(0xffffffffu, updated);
