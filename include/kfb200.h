@@ -34,6 +34,7 @@ typedef struct kfb_ctx kfb_ctx;
 #define KFB_FLAG_TRACK_STATUS   0x2u   /* keep the per-pixel ICP status plane that renderTrack visualises           */
 #define KFB_FLAG_NO_GRAPHS      0x4u   /* do not capture per-frame work into CUDA graphs                              */
 #define KFB_FLAG_INTEGRATE_NO_CULL 0x8u /* integrate visits every voxel with the reference's full expression (A/B check) */
+#define KFB_FLAG_RAYCAST_NO_SKIP 0x10u  /* raycast evaluates every sample (no brick flags) (A/B check)                    */
 
 typedef struct kfb_config {
 	uint32_t compute_w, compute_h;      /* Kfusion ctor `inputSize` = computation size   kernels.h:99-101 */

@@ -90,6 +90,8 @@ struct kfb_ctx {
 	unsigned int* d_dmax;       // two slots: bit pattern of max(floatDepth), written by preprocess (ping-pong)
 	uint32_t int_zchunk;        // integrate piece length override (KFB_INT_ZCHUNK, tuning)
 	uint2* d_queue; size_t queue_cap;   // integrate work list
+	BrickMap brick;             // brick flags for the raycaster (whole-volume contexts only)
+	bool brick_off;
 	unsigned int* d_queue_ctr;  // 2 slots x {count, head}
 	int int_grid;               // persistent CTAs of k_integrate_run
 	uint64_t int_launches;
@@ -168,6 +170,7 @@ static int launch_init_volume(kfb_ctx* c) {
 	const size_t n = c->slab_voxels, n4 = n / 4;
 	k_init_volume<<<148 * 8, 256, 0, c->stream>>>((uint4*) c->d_vol, n4, c->d_vol, n);
 	LAUNCHED(c);
+	if (c->brick.flag) CK(cudaMemsetAsync(c->brick.flag, 0, (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz, c->stream));   // 32766 everywhere
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -208,6 +211,7 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	kfb_ctx* c = new kfb_ctx();
 	memset(&c->st, 0, sizeof c->st);
 	c->cfg = *cfg;
+	{ const char* e = getenv("KFB_FLAGS"); if (e) c->cfg.flags |= (uint32_t) strtoul(e, nullptr, 0); }   // experiments: OR extra flags in
 	c->device = cfg->device;
 	c->cw = cfg->compute_w; c->ch = cfg->compute_h;
 	c->levels = cfg->n_levels;
@@ -310,6 +314,12 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	c->view_all.rdx = 1.0f / cfg->volume_dim[0]; c->view_all.rdy = 1.0f / cfg->volume_dim[1]; c->view_all.rdz = 1.0f / cfg->volume_dim[2];
 	c->view_all.fastdiv = (kfb_fastdiv_ok(cfg->volume_dim[0]) && kfb_fastdiv_ok(cfg->volume_dim[1]) && kfb_fastdiv_ok(cfg->volume_dim[2])) ? 1 : 0;
 	for (int i = 0; i < KFB_MAX_SLABS; ++i) c->peer_ptrs[i] = nullptr;
+	memset(&c->brick, 0, sizeof c->brick); c->brick_off = false;
+	if (c->z0 == 0 && c->z1 == cfg->volume_res[2] && !(c->cfg.flags & KFB_FLAG_RAYCAST_NO_SKIP)) {
+		c->brick.bnx = (cfg->volume_res[0] + 7) / 8; c->brick.bny = (cfg->volume_res[1] + 7) / 8; c->brick.bnz = (cfg->volume_res[2] + 7) / 8;
+		CK(cudaMalloc(&c->brick.flag, (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz));
+		c->view_all.brick = c->brick.flag; c->view_all.bnx = c->brick.bnx; c->view_all.bny = c->brick.bny;
+	}
 	int rc = launch_init_volume(c);
 	if (rc) return rc;
 	CK(cudaStreamSynchronize(c->stream));
@@ -323,6 +333,7 @@ int kfb_destroy(kfb_ctx* c) {
 	cudaStreamSynchronize(c->stream);
 	for (int i = 0; i < c->n_reg; ++i) cudaHostUnregister((void*) c->reg_ptr[i]);
 	for (int i = 0; i < KFB_MAX_SLABS; ++i) if (c->peer_ptrs[i]) cudaIpcCloseMemHandle(c->peer_ptrs[i]);
+	if (c->brick.flag) cudaFree(c->brick.flag);
 	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_floatDepth);
 	for (int l = 0; l < c->levels; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
 	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax); cudaFree(c->d_queue_ctr); if (c->d_queue) cudaFree(c->d_queue);
@@ -610,6 +621,12 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	p.invTrack = toMat(invTrack); p.K = toMat(K);
 	p.mu = mu; p.maxweight = maxweight;
 	p.cull = (c->cfg.flags & KFB_FLAG_INTEGRATE_NO_CULL) ? 0 : 1;
+	p.brick = c->brick;
+	if (maxweight > 200.f && c->brick.flag) {
+		// the flagging rule in k_integrate_run assumes w + 1 <= 201; beyond that stop using (and maintaining) the flags
+		c->view_all.brick = nullptr; p.brick.flag = nullptr; c->brick_off = true;
+	}
+	if (c->brick_off) p.brick.flag = nullptr;
 	p.dmax = (c->dmax_slot >= 0) ? reinterpret_cast<const float*>(c->d_dmax + c->dmax_slot) : nullptr;
 	const uint32_t slot = (uint32_t) (c->integrate_count % NUPD_SLOTS);
 	if (c->integrate_count >= NUPD_SLOTS) CK(cudaMemsetAsync(c->d_nupd + slot, 0, sizeof(unsigned long long), c->stream));
@@ -870,6 +887,12 @@ int kfb_write_buffer(kfb_ctx* c, int which, int level, const void* src, size_t b
 	if (which == KFB_BUF_FLOATDEPTH) c->dmax_slot = -1;   // the cached max no longer describes this image
 	CK(cudaStreamSynchronize(c->stream));
 	CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
+	if (which == KFB_BUF_VOLUME && c->brick.flag) {   // the flags must describe the volume the raycaster will read
+		CK(cudaMemsetAsync(c->brick.flag, 0, (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz, c->stream));
+		k_brick_rebuild<<<148 * 8, 256, 0, c->stream>>>(c->brick, c->d_vol, c->cfg.volume_res[0], c->cfg.volume_res[1], c->cfg.volume_res[2]);
+		LAUNCHED(c);
+		CK(cudaGetLastError());
+	}
 	return 0;
 }
 
@@ -919,6 +942,7 @@ int kfb_slab_import(kfb_ctx* c, int rank, int world, const uint8_t* handles64, c
 	CK(cudaSetDevice(c->device));
 	c->rank = rank; c->world = world;
 	c->view_all.n_slabs = world;
+	c->view_all.brick = nullptr;   // flags are per whole-volume context; peers' slabs are read without skipping
 	for (int r = 0; r < world; ++r) {
 		c->view_all.slab_z[r] = z_begin[r];
 		if (r == rank) { c->view_all.slab_ptr[r] = c->d_vol; continue; }

@@ -596,6 +596,42 @@ __global__ void __launch_bounds__(TR_THREADS, 2) k_icp(IcpParams p) {
 }
 
 // ------------------------------------------------------------------------------------------
+// Brick flags: one byte per 8^3 voxels, set (never cleared) as soon as any voxel of the brick — or of the
+// one-voxel halo on its upper sides, so that the 2x2x2 taps of a trilinear sample whose base voxel lies in
+// the brick are all covered — holds a tsdf below BRICK_T.  A clear flag therefore PROVES that every tap of
+// such a sample is >= BRICK_T, i.e. the interpolated value is >= 0.82 > 0.8: the raycaster's decisions for
+// that sample (`f < 0` and `f < 0.8`, cpp/kernels.cpp:711-714) are known without reading a voxel.
+// Maintained by integrate (and rebuilt when a volume is written from the host); 256 KB at 512^3.
+// ------------------------------------------------------------------------------------------
+#define BRICK_T 27000
+#define BRICK_SHIFT 3
+struct BrickMap {
+	unsigned char* flag;     // [bnz][bny][bnx]; nullptr = not maintained (multi-slab volumes)
+	uint32_t bnx, bny, bnz;
+};
+__device__ __noinline__ void brick_mark(const BrickMap b, uint32_t x, uint32_t y, uint32_t z) {
+	const uint32_t bx1 = x >> BRICK_SHIFT, by1 = y >> BRICK_SHIFT, bz1 = z >> BRICK_SHIFT;
+	const uint32_t bx0 = (((x & 7u) == 0u) && x) ? bx1 - 1 : bx1, by0 = (((y & 7u) == 0u) && y) ? by1 - 1 : by1,
+			bz0 = (((z & 7u) == 0u) && z) ? bz1 - 1 : bz1;
+	for (uint32_t bz = bz0; bz <= bz1; ++bz)
+		for (uint32_t by = by0; by <= by1; ++by)
+			for (uint32_t bx = bx0; bx <= bx1; ++bx) {
+				unsigned char* f = b.flag + ((size_t) bz * b.bny + by) * b.bnx + bx;
+				if (*f == 0) *f = 1;
+			}
+}
+// rebuild from a volume (after kfb_write_buffer / for tests)
+__global__ void __launch_bounds__(256) k_brick_rebuild(BrickMap b, const short2* __restrict__ vol, uint32_t sx, uint32_t sy, uint32_t sz) {
+	const size_t n = (size_t) sx * sy * sz, stride = (size_t) gridDim.x * blockDim.x;
+	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+		if (vol[i].x < BRICK_T) {
+			const uint32_t x = (uint32_t) (i % sx), y = (uint32_t) ((i / sx) % sy), z = (uint32_t) (i / ((size_t) sx * sy));
+			brick_mark(b, x, y, z);
+		}
+	}
+}
+
+// ------------------------------------------------------------------------------------------
 // integrateKernel (cpp/kernels.cpp:628-673): TSDF running average over the voxels that
 // project into the depth image.  The reference walks each (x,y) column from z = 0 and
 // advances `pos` / `cameraX` by REPEATED fp32 addition; reproducing those exact values is
@@ -631,6 +667,7 @@ struct IntegrateParams {
 	const float* dmax;         // optional: max of the depth image (device scalar); nullptr = unknown
 	int cull;                  // 0 = visit every voxel (debug / A-B), 1 = interval + fast tests
 	unsigned long long* n_upd;
+	BrickMap brick;            // flags for the raycaster (flag == nullptr: not maintained)
 	uint2* queue;              // work list: warp-columns with a non-empty visited interval
 	unsigned int* piece_ctr;   // per work-list entry: next unclaimed piece
 	unsigned int* queue_count; // [0] items appended by the plan pass, [1] next item (this frame's slot)
@@ -741,6 +778,7 @@ __global__ void __launch_bounds__(256) k_integrate_plan(IntegrateParams p) {
 	za = __reduce_min_sync(0xffffffffu, za);
 	zb = __reduce_max_sync(0xffffffffu, zb);
 	if (za >= zb) return;
+	za = max((int) p.z_begin, za & ~(INT_U - 1));   // batches on multiples of INT_U (brick layers); still conservative
 	if (threadIdx.x == 0) {
 		const uint32_t e = atomicAdd(p.queue_count, 1u);
 		p.queue[e] = make_uint2(blockIdx.x | (y << 16), (uint32_t) za | ((uint32_t) zb << 16));
@@ -754,7 +792,10 @@ __global__ void __launch_bounds__(256) k_integrate_plan(IntegrateParams p) {
 // progress (they replay the additions up to their piece), which removes the tail.  Every piece is processed
 // exactly once.
 #define INT_LAPS 4
-__global__ void __launch_bounds__(256, 4) k_integrate_run(IntegrateParams p) {
+#ifndef KFB_INT_MINBLOCKS
+#define KFB_INT_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run(IntegrateParams p) {
 	const uint32_t lane = threadIdx.x & 31;
 	const float dwm1 = (float) (p.dw - 1), dhm1 = (float) (p.dh - 1);
 	// fast tests need: mu > 0, image small enough that an approximate quotient beyond +-2048 is conclusively outside
@@ -807,6 +848,7 @@ __global__ void __launch_bounds__(256, 4) k_integrate_run(IntegrateParams p) {
 		for (int z = za; z < zb; z += INT_U, col += INT_U * plane) {
 			float sdf[INT_U];
 			short2 v[INT_U];
+			unsigned int low = 0;   // bit u: this lane stored a tsdf below BRICK_T in slice z + u
 #pragma unroll
 			for (int u = 0; u < INT_U; ++u) {
 				const float Px = f2_lo(A), Py = f2_hi(A), Pz = f2_lo(B), Cx = f2_hi(B), Cy = f2_lo(C), Cz = f2_hi(C);
@@ -834,6 +876,33 @@ __global__ void __launch_bounds__(256, 4) k_integrate_run(IntegrateParams p) {
 #pragma unroll
 			for (int u = 0; u < INT_U; ++u)
 				if (sdf[u] > -2.f) v[u] = __ldcs(col + u * plane);
+#pragma unroll
+			for (int u = 0; u < INT_U; ++u) low |= (sdf[u] > -2.f && sdf[u] < 0.9f) ? (1u << u) : 0u;
+			// Brick flags for the raycaster, while the voxel loads are in flight.  A stored tsdf can only fall below
+			// BRICK_T (0.824) in an update whose sdf is below 0.9: with sdf >= 0.9 the running average
+			// (w t + sdf) / (w + 1), w + 1 <= 101, either stays above 0.89 or rises by more than the 1 LSB the truncation
+			// can take away.  So flagging every slice that holds an update with sdf < 0.9 keeps the invariant
+			// "flag clear => every voxel of the brick (and halo) >= BRICK_T" without looking at the stored values.
+			// The warp's 32 voxels of a slice span 4 bricks in x (lanes 8k..8k+7 -> brick k; lane 8k also lies in the
+			// halo of brick k-1), one or two in y and in z: lanes 0..4 each flag one x-brick.
+			// Batches start at multiples of 8 when the flags are maintained (the plan pass aligns za), so a batch is
+			// one brick layer bz = z / 8 plus, through its first slice, the halo of layer bz - 1.
+			if (p.brick.flag) {
+				const unsigned int m_any = __ballot_sync(0xffffffffu, low != 0u), m_0 = __ballot_sync(0xffffffffu, low & 1u);
+				if (m_any && lane < 5) {
+					const int j = (int) lane - 1;   // x-brick relative to the warp's first brick: -1 (halo of the previous tile) .. 3
+					unsigned int any = 0, first = 0;
+					if (j >= 0) { any = (m_any >> (8 * j)) & 0xffu; first = (m_0 >> (8 * j)) & 0xffu; }
+					if (j < 3) { any |= (m_any >> (8 * (j + 1))) & 1u; first |= (m_0 >> (8 * (j + 1))) & 1u; }   // next brick's first voxel: halo
+					const uint32_t xb = (item.x & 0xffffu) * 4, bx = xb + (uint32_t) j;
+					if (any && (j >= 0 || xb > 0) && bx < p.brick.bnx) {
+						const uint32_t by1 = y >> BRICK_SHIFT, by0 = (((y & 7u) == 0u) && y) ? by1 - 1 : by1;
+						const uint32_t bz1 = (uint32_t) z >> BRICK_SHIFT, bz0 = (first && bz1) ? bz1 - 1 : bz1;
+						for (uint32_t bz = bz0; bz <= bz1; ++bz)
+							for (uint32_t by = by0; by <= by1; ++by) p.brick.flag[((size_t) bz * p.brick.bny + by) * p.brick.bnx + bx] = 1;
+					}
+				}
+			}
 #pragma unroll
 			for (int u = 0; u < INT_U; ++u)
 				if (sdf[u] > -2.f) {
@@ -869,6 +938,8 @@ struct VolView {
 	// over all 2^23 significands on the host at kfb_create, see kfb_fastdiv_ok)
 	float rdx, rdy, rdz;
 	int fastdiv;
+	const unsigned char* brick;   // brick flags (see BrickMap) or nullptr
+	uint32_t bnx, bny;
 };
 
 // fl(a / d) for a per-launch constant d with rd = fl(1/d): q = a*rd, r = fma(-d, q, a) (exact), q + r*rd rounds
@@ -901,16 +972,29 @@ __device__ __forceinline__ const short2* vol_plane(const VolView& v, int z) {   
 	return v.slab_ptr[s] + (size_t) ((uint32_t) z - v.slab_z[s]) * v.sx * v.sy;
 }
 
-__device__ __forceinline__ float vol_interp(const VolView& v, float3 pos) {  // commons.h:191-213
+struct VolCell { int bx, by, bz; float fx, fy, fz; };
+__device__ __forceinline__ VolCell vol_cell(const VolView& v, float3 pos) {   // commons.h:192-197: scaled position -> base voxel + fraction
 	const float spx = div_const(pos.x * (float) v.sx, v.dx, v.rdx, v.fastdiv) - 0.5f;
 	const float spy = div_const(pos.y * (float) v.sy, v.dy, v.rdy, v.fastdiv) - 0.5f;
 	const float spz = div_const(pos.z * (float) v.sz, v.dz, v.rdz, v.fastdiv) - 0.5f;
 	const float flx = floorf(spx), fly = floorf(spy), flz = floorf(spz);
+	VolCell c;
 	// base is in [-1, N-1] for every position the reference samples (inside the volume box); clamping the base itself
 	// changes nothing there and keeps the taps in bounds for any other position (NaN pose, renderVolume's 2x far plane)
-	const int bx = kmini(kmaxi((int) flx, -1), (int) v.sx - 1), by = kmini(kmaxi((int) fly, -1), (int) v.sy - 1),
-			bz = kmini(kmaxi((int) flz, -1), (int) v.sz - 1);
-	const float fx = spx - flx, fy = spy - fly, fz = spz - flz;
+	c.bx = kmini(kmaxi((int) flx, -1), (int) v.sx - 1); c.by = kmini(kmaxi((int) fly, -1), (int) v.sy - 1);
+	c.bz = kmini(kmaxi((int) flz, -1), (int) v.sz - 1);
+	c.fx = spx - flx; c.fy = spy - fly; c.fz = spz - flz;
+	return c;
+}
+// true: all 8 taps of this cell are proven >= BRICK_T (the sample is >= 0.82) without touching the volume
+__device__ __forceinline__ bool vol_cell_free(const VolView& v, const VolCell& c) {
+	if (!v.brick) return false;
+	const uint32_t bx = (uint32_t) kmaxi(c.bx, 0) >> BRICK_SHIFT, by = (uint32_t) kmaxi(c.by, 0) >> BRICK_SHIFT, bz = (uint32_t) kmaxi(c.bz, 0) >> BRICK_SHIFT;
+	return __ldg(v.brick + ((size_t) bz * v.bny + by) * v.bnx + bx) == 0;
+}
+__device__ __forceinline__ float vol_interp_cell(const VolView& v, const VolCell& c) {  // commons.h:198-212
+	const int bx = c.bx, by = c.by, bz = c.bz;
+	const float fx = c.fx, fy = c.fy, fz = c.fz;
 	const int lx = kmaxi(bx, 0), ly = kmaxi(by, 0), lz = kmaxi(bz, 0);
 	const int ux = kmini(bx + 1, (int) v.sx - 1), uy = kmini(by + 1, (int) v.sy - 1), uz = kmini(bz + 1, (int) v.sz - 1);
 	// two slice bases (z may straddle slabs), two row offsets, two column offsets: 8 taps from 3 adds each
@@ -924,6 +1008,9 @@ __device__ __forceinline__ float vol_interp(const VolView& v, float3 pos) {  // 
 	const float gx = 1 - fx, gy = 1 - fy, gz = 1 - fz;
 	return (((v000 * gx + v100 * fx) * gy + (v010 * gx + v110 * fx) * fy) * gz
 			+ ((v001 * gx + v101 * fx) * gy + (v011 * gx + v111 * fx) * fy) * fz) * 0.00003051944088f;
+}
+__device__ __forceinline__ float vol_interp(const VolView& v, float3 pos) {  // commons.h:191-213
+	return vol_interp_cell(v, vol_cell(v, pos));
 }
 
 __device__ __forceinline__ float3 vol_grad(const VolView& v, float3 pos) {  // commons.h:215-301
@@ -975,13 +1062,22 @@ __device__ __forceinline__ float3 raycast_one(const VolView& v, uint32_t px, uin
 		float f_t = vol_interp(v, origin + direction * t);
 		float f_tt = 0;
 		if (f_t > 0) {
+			// Samples whose cell lies in a brick with a clear flag are >= 0.82: neither `f_tt < 0` nor `f_tt < 0.8`
+			// can fire, so the step is taken without reading the volume.  The value itself is only ever needed as
+			// f_t of the zero crossing: it is then evaluated at the remembered t (same expression, same value).
+			bool lazy = false;
+			float t_lazy = t;
 			for (; t < tfar; t += stepsize) {
-				f_tt = vol_interp(v, origin + direction * t);
+				const VolCell c = vol_cell(v, origin + direction * t);
+				if (vol_cell_free(v, c)) { f_tt = 1.f; lazy = true; t_lazy = t; continue; }
+				f_tt = vol_interp_cell(v, c);
 				if (f_tt < 0) break;
 				if (f_tt < 0.8f) stepsize = step;
 				f_t = f_tt;
+				lazy = false;
 			}
 			if (f_tt < 0) {
+				if (lazy) f_t = vol_interp(v, origin + direction * t_lazy);
 				t = t + stepsize * f_tt / (f_t - f_tt);
 				*tw = t;
 				return origin + direction * t;

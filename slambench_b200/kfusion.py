@@ -21,6 +21,7 @@ FLAG_ICP_HOST_SOLVE = 0x1
 FLAG_TRACK_STATUS = 0x2
 FLAG_NO_GRAPHS = 0x4
 FLAG_INTEGRATE_NO_CULL = 0x8
+FLAG_RAYCAST_NO_SKIP = 0x10
 
 (BUF_VOLUME, BUF_VERTEX, BUF_NORMAL, BUF_FLOATDEPTH, BUF_SCALEDDEPTH, BUF_INVERTEX, BUF_INNORMAL,
  BUF_REDUCTION, BUF_TRACKSTATUS, BUF_RAYCASTPOSE, BUF_OLDPOSE, BUF_GAUSSIAN, BUF_INPUTDEPTH, BUF_REDUCTION_DEV) = range(14)
@@ -64,6 +65,8 @@ def load_library(path: str | None = None) -> C.CDLL:
     global _lib
     if _lib is not None and path is None:
         return _lib
+    if path is None and os.environ.get("KFB_LIB"):
+        path = os.environ["KFB_LIB"]   # an alternative build of the same library (tuning experiments)
     if path is None:
         path = _build.LIB
         if not os.path.exists(path) or os.environ.get("KFB_REBUILD"):

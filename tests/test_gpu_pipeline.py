@@ -199,3 +199,38 @@ def test_zero_iteration_pyramid_levels(port, seq16):
     p_gpu, t_gpu, i_gpu = run_gpu_pipeline(depth, 8, 64, pyramid=pyr)
     assert t_gpu == t_cpu and i_gpu == i_cpu
     assert np.abs(p_gpu - p_cpu).max() <= 1e-4
+
+
+def test_raycast_brick_skipping_is_exact(seq16):
+    """Brick flags let the raycaster step over samples proven >= 0.82 without reading the volume.  The maps, poses
+    and flags of a whole run must be bit-identical to the run that evaluates every sample (KFB_FLAG_RAYCAST_NO_SKIP),
+    also for the 2x-far-plane volume render and after the volume is replaced from the host (flags rebuilt)."""
+    depth, _ = seq16
+    n = 12
+    snaps = {}
+
+    def grab(tag):
+        def f(fr, g):
+            if fr >= 3:
+                snaps.setdefault(tag, []).append((g.read(kf.BUF_VERTEX).copy(), g.read(kf.BUF_NORMAL).copy()))
+            if fr == n - 1:
+                snaps[tag + "_render"] = g.renderVolume(0, 1, K, 0.075)
+                snaps[tag + "_vol"] = g.read(kf.BUF_VOLUME)
+        return f
+
+    pa, ta, ia = run_gpu_pipeline(depth, n, 256, on_frame=grab("skip"))
+    pb, tb, ib = run_gpu_pipeline(depth, n, 256, flags=kf.FLAG_RAYCAST_NO_SKIP, on_frame=grab("full"))
+    assert ta == tb and ia == ib and np.array_equal(pa, pb)
+    for (va, na), (vb, nb) in zip(snaps["skip"], snaps["full"]):
+        assert np.array_equal(va.view(np.uint32), vb.view(np.uint32)) and np.array_equal(na.view(np.uint32), nb.view(np.uint32))
+    assert np.array_equal(snaps["skip_render"], snaps["full_render"])
+    assert np.array_equal(snaps["skip_vol"], snaps["full_vol"])
+    # host-written volume: the flags are rebuilt from it
+    with kf.Kfusion((640, 480), 256, 4.8, T0, (10, 5, 4)) as a, kf.Kfusion((640, 480), 256, 4.8, T0, (10, 5, 4), flags=kf.FLAG_RAYCAST_NO_SKIP) as b:
+        view = a.matmul(pa[-1], a.inverseCameraMatrix(K))
+        for g in (a, b):
+            g.write(kf.BUF_VOLUME, snaps["full_vol"])
+            g.raycastKernel(view)
+        assert np.array_equal(a.read(kf.BUF_VERTEX).view(np.uint32), b.read(kf.BUF_VERTEX).view(np.uint32))
+        assert np.array_equal(a.read(kf.BUF_NORMAL).view(np.uint32), b.read(kf.BUF_NORMAL).view(np.uint32))
+        assert (a.read(kf.BUF_NORMAL)[..., 0] != -2).mean() > 0.9
