@@ -72,6 +72,16 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def traffic_bytes(args):
+    """DRAM bytes per integrate launch from the committed ncu capture (profiles/integrate_traffic.json), or null."""
+    if args.traffic_bytes is not None:
+        return args.traffic_bytes
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "integrate_traffic.json"))).get(str(args.volume))
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------- clocks
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled from a
@@ -299,8 +309,8 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
         achieved = alg_bytes / t_int_s / 1e9 if t_int_s > 0 else 0.0
         full_sweep_bytes = 8.0 * args.volume ** 3 + 4.0 * P_PIX
         roof = {
-            "bound": "hbm", "kernel": "k_integrate", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": args.traffic_bytes, "peak_source": peak_src,
+            "bound": "hbm", "kernel": "k_integrate_plan + k_integrate_run", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic_bytes(args), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": t_int_s * 1e6,
             "n_upd_per_launch": st["voxels_updated_total"] / n_int,
             "full_sweep_gbs": full_sweep_bytes / t_int_s / 1e9 if t_int_s > 0 else 0.0,
