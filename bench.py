@@ -361,11 +361,13 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
     K = np.array(synth.K_DEFAULT, np.float32)
     T0 = (np.array(synth.INIT_POS_FACTOR, np.float32) * np.float32(VOLUME_DIM)).astype(np.float32)
     n = args.warmup + args.steps
-    depth_np, gt = synth.make_sequence(n, long_run=False if n <= 400 else None)
+    n_diag = 6                                    # extra frames for the per-stage breakdown (after the timed region)
+    depth_np, gt = synth.make_sequence(n + n_diag, long_run=False if n + n_diag <= 400 else None)
     host = torch.from_numpy(depth_np).pin_memory()
     depth_np = host.numpy()
     with sharded.ShardedKfusion((W_IMG, H_IMG), args.volume, VOLUME_DIM, T0, PYRAMID, rank=rank, world=world, device=local_rank,
-                                icp_mode=args.icp_mode) as s:
+                                icp_mode=args.icp_mode, balance_k=None if args.even_slabs else K,
+                                balance_far=float(depth_np[0].max()) / 1000.0) as s:
         g = s.local
         stream = g.torch_stream(torch)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -402,6 +404,19 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
         err = float(np.abs(s.getPose()[:3, 3] - gt[n - 1][:3, 3]).max())
+        # per-stage breakdown: the same calls with a full sync after each stage (host-visible time, max over ranks)
+        stage = np.zeros(4)
+        for f in range(n, n + n_diag):
+            marks = [time.perf_counter()]
+            for call in (lambda: s.preprocessing(depth_np[f]), lambda: s.tracking(K, ICP_THRESHOLD, 1, f),
+                         lambda: s.integration(K, 1, MU, f), lambda: s.raycasting(K, MU, f)):
+                call()
+                s.synchroniseDevices()
+                torch.cuda.synchronize()
+                marks.append(time.perf_counter())
+            stage += np.diff(marks) * 1e3 / n_diag
+        tstage = torch.tensor(stage, dtype=torch.float64, device=f"cuda:{local_rank}")
+        dist.all_reduce(tstage, op=dist.ReduceOp.MAX)
         if rank == 0:
             peak, peak_src = peaks()
             ms_all = float(tmax[0])
@@ -414,6 +429,7 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(args.volume), "volume": args.volume, "frames": n,
                            "parallelism": f"z-slab x{world}: integrate local, raycast via NVLink peer slabs + NCCL all-gather, ICP {args.icp_mode}",
+                           "slabs": [list(z) for z in s.slabs],
                            "tracked_frames": int(tracked), "final_pose_err_m": err},
                 "e2e": {"value": args.steps / (ms_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W_IMG * H_IMG * 2,
                         "d2h_bytes_per_step": st["d2h_bytes"] / args.steps},
@@ -421,6 +437,9 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
                 "roofline": {"bound": "hbm", "kernel": "k_integrate_run", "achieved": alg / t_int / 1e9, "peak": peak * world, "unit": "GB/s",
                              "frac": alg / t_int / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src + f" x{world}",
                              "us_per_launch": t_int * 1e6},
+                "stage_ms_per_frame": {"preprocess": float(tstage[0]), "track": float(tstage[1]),
+                                       "integrate+flag merge": float(tstage[2]), "raycast+all-gather": float(tstage[3]),
+                                       "note": "synchronised after every stage, max over ranks"},
             }
             print(json.dumps(line), flush=True)
     dist.destroy_process_group()
@@ -439,6 +458,7 @@ def main():
     ap.add_argument("--mode", default="sequences", choices=["sequences", "sharded"],
                     help="N > 1: one independent sequence per GPU (weak scaling, default) or ONE sequence on a z-slab sharded volume (strong)")
     ap.add_argument("--icp-mode", default="replicated", choices=["replicated", "allreduce"])
+    ap.add_argument("--even-slabs", action="store_true", help="sharded mode: equal z-slabs instead of the load-aware boundaries")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes/launch of k_integrate from the ncu capture in profiles/")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -35,6 +35,8 @@ typedef struct kfb_ctx kfb_ctx;
 #define KFB_FLAG_NO_GRAPHS      0x4u   /* do not capture per-frame work into CUDA graphs                              */
 #define KFB_FLAG_INTEGRATE_NO_CULL 0x8u /* integrate visits every voxel with the reference's full expression (A/B check) */
 #define KFB_FLAG_RAYCAST_NO_SKIP 0x10u  /* raycast evaluates every sample (no brick flags) (A/B check)                    */
+#define KFB_FLAG_BRICKS_MERGED 0x20u    /* z-slab mode: the caller merges (element-wise max over ranks) KFB_BUF_BRICKFLAGS between
+                                          integrate and raycast, so the raycaster may skip over peers' free space too          */
 
 typedef struct kfb_config {
 	uint32_t compute_w, compute_h;      /* Kfusion ctor `inputSize` = computation size   kernels.h:99-101 */
@@ -75,7 +77,8 @@ enum kfb_buffer {
 	KFB_BUF_OLDPOSE = 10,     /* float[16] (host)                                         `oldPose`          */
 	KFB_BUF_GAUSSIAN = 11,    /* float[5]                                                 `gaussian`         */
 	KFB_BUF_INPUTDEPTH = 12,  /* uint16[in_w*in_h] device copy of the last sensor frame                      */
-	KFB_BUF_REDUCTION_DEV = 13 /* float[32] DEVICE copy of the last track+reduce result (multi-GPU all-reduce operand) */
+	KFB_BUF_REDUCTION_DEV = 13, /* float[32] DEVICE copy of the last track+reduce result (multi-GPU all-reduce operand) */
+	KFB_BUF_BRICKFLAGS = 14   /* uint8[ceil(N/8)^3] brick flags of the WHOLE volume (see KFB_FLAG_BRICKS_MERGED)            */
 };
 
 int kfb_abi_version(void);

@@ -315,7 +315,8 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	c->view_all.fastdiv = (kfb_fastdiv_ok(cfg->volume_dim[0]) && kfb_fastdiv_ok(cfg->volume_dim[1]) && kfb_fastdiv_ok(cfg->volume_dim[2])) ? 1 : 0;
 	for (int i = 0; i < KFB_MAX_SLABS; ++i) c->peer_ptrs[i] = nullptr;
 	memset(&c->brick, 0, sizeof c->brick); c->brick_off = false;
-	if (c->z0 == 0 && c->z1 == cfg->volume_res[2] && !(c->cfg.flags & KFB_FLAG_RAYCAST_NO_SKIP)) {
+	const bool whole = (c->z0 == 0 && c->z1 == cfg->volume_res[2]);
+	if ((whole || (c->cfg.flags & KFB_FLAG_BRICKS_MERGED)) && !(c->cfg.flags & KFB_FLAG_RAYCAST_NO_SKIP)) {
 		c->brick.bnx = (cfg->volume_res[0] + 7) / 8; c->brick.bny = (cfg->volume_res[1] + 7) / 8; c->brick.bnz = (cfg->volume_res[2] + 7) / 8;
 		CK(cudaMalloc(&c->brick.flag, (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz));
 		c->view_all.brick = c->brick.flag; c->view_all.bnx = c->brick.bnx; c->view_all.bny = c->brick.bny;
@@ -851,6 +852,9 @@ static int resolve_buffer(kfb_ctx* c, int which, int level, void** ptr, size_t* 
 	case KFB_BUF_GAUSSIAN: *ptr = c->gaussian; *bytes = 20; *host = true; break;
 	case KFB_BUF_INPUTDEPTH: *ptr = c->d_input; *bytes = c->input_bytes; break;
 	case KFB_BUF_REDUCTION_DEV: *ptr = c->d_out32; *bytes = 32 * 4; break;
+	case KFB_BUF_BRICKFLAGS:
+		if (!c->brick.flag) return set_err(KFB_E_STATE, "brick flags are not maintained by this context");
+		*ptr = c->brick.flag; *bytes = (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz; break;
 	default: return set_err(KFB_E_ARG, "unknown buffer %d", which);
 	}
 	return 0;
@@ -889,7 +893,7 @@ int kfb_write_buffer(kfb_ctx* c, int which, int level, const void* src, size_t b
 	CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
 	if (which == KFB_BUF_VOLUME && c->brick.flag) {   // the flags must describe the volume the raycaster will read
 		CK(cudaMemsetAsync(c->brick.flag, 0, (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz, c->stream));
-		k_brick_rebuild<<<148 * 8, 256, 0, c->stream>>>(c->brick, c->d_vol, c->cfg.volume_res[0], c->cfg.volume_res[1], c->cfg.volume_res[2]);
+		k_brick_rebuild<<<148 * 8, 256, 0, c->stream>>>(c->brick, c->d_vol, c->cfg.volume_res[0], c->cfg.volume_res[1], c->z1 - c->z0, c->z0);
 		LAUNCHED(c);
 		CK(cudaGetLastError());
 	}
@@ -942,7 +946,8 @@ int kfb_slab_import(kfb_ctx* c, int rank, int world, const uint8_t* handles64, c
 	CK(cudaSetDevice(c->device));
 	c->rank = rank; c->world = world;
 	c->view_all.n_slabs = world;
-	c->view_all.brick = nullptr;   // flags are per whole-volume context; peers' slabs are read without skipping
+	// each rank flags only what ITS slices touch: without the caller's merge the raycaster must not skip
+	if (!(c->cfg.flags & KFB_FLAG_BRICKS_MERGED)) c->view_all.brick = nullptr;
 	for (int r = 0; r < world; ++r) {
 		c->view_all.slab_z[r] = z_begin[r];
 		if (r == rank) { c->view_all.slab_ptr[r] = c->d_vol; continue; }

@@ -621,11 +621,11 @@ __device__ __noinline__ void brick_mark(const BrickMap b, uint32_t x, uint32_t y
 			}
 }
 // rebuild from a volume (after kfb_write_buffer / for tests)
-__global__ void __launch_bounds__(256) k_brick_rebuild(BrickMap b, const short2* __restrict__ vol, uint32_t sx, uint32_t sy, uint32_t sz) {
+__global__ void __launch_bounds__(256) k_brick_rebuild(BrickMap b, const short2* __restrict__ vol, uint32_t sx, uint32_t sy, uint32_t sz, uint32_t z_begin) {
 	const size_t n = (size_t) sx * sy * sz, stride = (size_t) gridDim.x * blockDim.x;
 	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
 		if (vol[i].x < BRICK_T) {
-			const uint32_t x = (uint32_t) (i % sx), y = (uint32_t) ((i / sx) % sy), z = (uint32_t) (i / ((size_t) sx * sy));
+			const uint32_t x = (uint32_t) (i % sx), y = (uint32_t) ((i / sx) % sy), z = z_begin + (uint32_t) (i / ((size_t) sx * sy));
 			brick_mark(b, x, y, z);
 		}
 	}

@@ -10,7 +10,9 @@ the single-GPU C ABI (include/kfb200.h):
   raycast     pixels are partitioned (row bands): rank r marches ITS rays through the WHOLE volume,
               reading the other ranks' slabs through CUDA-IPC peer pointers (NVLink P2P loads inside
               k_raycast); the bands of the vertex / normal maps are then all-gathered (NCCL) so that
-              every rank holds the full ICP reference.
+              every rank holds the full ICP reference.  The brick flags that let the raycaster step over
+              free space are merged over the ranks (all-reduce MAX, 2 MB at 1024^3) right after integrate,
+              so most samples never touch a peer's memory.
   track       "replicated" (default): every rank runs the whole persistent ICP kernel on all pixels —
               bitwise identical poses on every rank, zero collectives (ICP is ~0.15 ms; a per-iteration
               all-reduce costs more than it saves).
@@ -31,16 +33,88 @@ import numpy as np
 from . import kfusion as kf
 
 
-def slab_bounds(n_z: int, world: int) -> list[tuple[int, int]]:
-    """Contiguous z-ranges, sizes differing by at most one slice, in rank order."""
-    if world < 1 or n_z < world:
+def slab_bounds(n_z: int, world: int, weights=None, align: int = 1) -> list[tuple[int, int]]:
+    """Contiguous z-ranges in rank order.  Without `weights`: sizes differing by at most one slice.  With
+    per-slice `weights` (expected integrate work, see frustum_slice_weights): boundaries (multiples of `align`)
+    that equalise the summed weight, every slab keeping at least `align` slices."""
+    if world < 1 or n_z < world * align:
         raise ValueError(f"cannot cut {n_z} slices into {world} slabs")
-    base, extra = divmod(n_z, world)
-    out, z = [], 0
-    for r in range(world):
-        n = base + (1 if r < extra else 0)
-        out.append((z, z + n))
-        z += n
+    if weights is None:
+        base, extra = divmod(n_z, world)
+        out, z = [], 0
+        for r in range(world):
+            n = base + (1 if r < extra else 0)
+            out.append((z, z + n))
+            z += n
+        return out
+    w = np.asarray(weights, np.float64)
+    if w.shape != (n_z,) or not np.all(w >= 0):
+        raise ValueError("weights must be one non-negative number per slice")
+    w = w + w.sum() * 0.02 / n_z + 1e-12          # a floor: empty regions still cost the raycaster's peer reads
+
+    # cost of a slab [a, b): its visited voxels (~100 warp-instructions per 32-voxel slice row) plus the replay of
+    # the reference's additions from z = 0 up to the slab for every column it visits (~3.4 per step)
+    def cost(a, b):
+        return 100.0 * w[a:b].sum() + 3.4 * a * w[a:b].max()
+
+    # minimise the largest slab cost: bisection on the bound, greedy cuts from the far end
+    cand = list(range(0, n_z + 1, align))
+    if cand[-1] != n_z:
+        cand.append(n_z)
+
+    def cuts_for(bound):
+        cuts, hi = [n_z], n_z
+        for _ in range(world - 1):
+            lo_ok = None
+            for a in reversed([c for c in cand if c < hi]):
+                if cost(a, hi) <= bound:
+                    lo_ok = a
+                else:
+                    break
+            if lo_ok is None or lo_ok == 0:
+                break
+            cuts.append(lo_ok)
+            hi = lo_ok
+        return cuts, cost(0, hi) <= bound
+
+    lo, hi_b = 0.0, cost(0, n_z)
+    for _ in range(40):
+        mid = 0.5 * (lo + hi_b)
+        if cuts_for(mid)[1]:
+            hi_b = mid
+        else:
+            lo = mid
+    cuts = sorted(set(cuts_for(hi_b)[0]) | {0})
+    # exactly `world` slabs: split the widest ones if the greedy pass needed fewer
+    while len(cuts) - 1 < world:
+        widths = [(cuts[i + 1] - cuts[i], i) for i in range(len(cuts) - 1)]
+        wd, i = max(widths)
+        mid = (cuts[i] + cuts[i + 1]) // 2 // align * align
+        if mid <= cuts[i] or mid >= cuts[i + 1]:
+            raise ValueError("cannot place the slab boundaries")
+        cuts.insert(i + 1, mid)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def frustum_slice_weights(n_z: int, volume_dim: float, pose, k, image_wh, far: float = 4.0, mu: float = 0.1):
+    """Expected integrate work per z-slice for a camera at `pose`: the area of the slice that projects into the
+    image at a depth the sensor can report (the voxels integrate visits, cpp/kernels.cpp:647-661).  Used once, at
+    set-up, to place the slab boundaries; the partition stays valid while the camera moves little compared with
+    the volume (it is only a load-balance heuristic: any partition gives the same voxels)."""
+    pose = np.asarray(pose, np.float64).reshape(4, 4)
+    fx, fy, cx, cy = [float(v) for v in k]
+    w, h = image_wh
+    n = 48                                                     # coarse grid over the slice
+    g = (np.arange(n) + 0.5) / n * volume_dim
+    X, Y = np.meshgrid(g, g)
+    Rinv, t = pose[:3, :3].T, pose[:3, 3]
+    out = np.zeros(n_z)
+    for z in range(n_z):
+        P = np.stack([X - t[0], Y - t[1], np.full_like(X, (z + 0.5) / n_z * volume_dim - t[2])], -1) @ Rinv.T
+        d = P[..., 2]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u, v = fx * P[..., 0] / d + cx, fy * P[..., 1] / d + cy
+        out[z] = np.count_nonzero((d > 1e-4) & (d < far + mu) & (u >= 0) & (u <= w - 1) & (v >= 0) & (v <= h - 1))
     return out
 
 
@@ -63,7 +137,8 @@ class ShardedKfusion:
     """`Kfusion` (kernels.h:83-195) over `world` GPUs; same method names and return values."""
 
     def __init__(self, inputSize, volumeResolution, volumeDimensions, initPose, pyramid=(10, 5, 4), *, rank: int, world: int,
-                 device: int = 0, icp_mode: str = "replicated", dist=None, local_factory=None, flags: int = 0):
+                 device: int = 0, icp_mode: str = "replicated", dist=None, local_factory=None, flags: int = 0,
+                 balance_k=None, balance_far: float = 4.0):
         if dist is None:
             import torch.distributed as dist  # noqa: PLC0415
         import torch  # noqa: PLC0415
@@ -74,11 +149,18 @@ class ShardedKfusion:
             raise ValueError(icp_mode)
         self.icp_mode = icp_mode
         vr = [int(volumeResolution)] * 3 if np.isscalar(volumeResolution) else [int(v) for v in volumeResolution]
-        self.slabs = slab_bounds(vr[2], world)
+        weights = None
+        if balance_k is not None:
+            # load-aware slab boundaries from the initial pose (identical on every rank: pure function of the arguments)
+            ip = np.asarray(initPose, np.float32)
+            pose0 = kf.identity_pose(ip) if ip.size == 3 else ip.reshape(4, 4)
+            vd = float(volumeDimensions) if np.isscalar(volumeDimensions) else float(volumeDimensions[2])
+            weights = frustum_slice_weights(vr[2], vd, pose0, balance_k, (int(inputSize[0]), int(inputSize[1])), far=balance_far)
+        self.slabs = slab_bounds(vr[2], world, weights, align=8 if weights is not None else 1)
         self.bands = row_bands(int(inputSize[1]), world)
         self.pyramid = tuple(int(i) for i in pyramid)
         make = local_factory or (lambda **kw: kf.Kfusion(inputSize, vr, volumeDimensions, initPose, self.pyramid, **kw))
-        self.local = make(device=device, slab=self.slabs[rank], flags=flags)
+        self.local = make(device=device, slab=self.slabs[rank], flags=flags | kf.FLAG_BRICKS_MERGED)
         self.computationSize = (int(inputSize[0]), int(inputSize[1]))
         # peer slabs: CUDA IPC handles travel through the (CPU) object collective
         handles = [None] * world
@@ -91,13 +173,15 @@ class ShardedKfusion:
         self._normal = self._view(kf.BUF_NORMAL, (h, w, 3))
         self._red = self._view(kf.BUF_REDUCTION_DEV, (32,))
         self._token = torch.zeros(1, device=self._vertex.device)
+        nb = [(v + 7) // 8 for v in vr]
+        self._bricks = None if (flags & kf.FLAG_RAYCAST_NO_SKIP) else self._view(kf.BUF_BRICKFLAGS, (nb[2], nb[1], nb[0]), "|u1")
         dist.barrier()
 
     # ------------------------------------------------------------------ plumbing
-    def _view(self, which, shape):
+    def _view(self, which, shape, typestr="<f4"):
         if hasattr(self.local, "tensor"):           # CPU stand-in used by the gloo tests
             return self.local.tensor(which)
-        return self.torch.as_tensor(_DevArray(self.local.device_ptr(which), shape, "<f4"), device=f"cuda:{self.device}")
+        return self.torch.as_tensor(_DevArray(self.local.device_ptr(which), shape, typestr), device=f"cuda:{self.device}")
 
     def _on_stream(self):
         if self._stream is None:
@@ -153,7 +237,12 @@ class ShardedKfusion:
     def integration(self, k, integration_rate: int, mu: float, frame: int) -> bool:
         done = self.local.integration(k, integration_rate, mu, frame)
         with self._on_stream():
-            self.dist.all_reduce(self._token)       # stream-ordered barrier: every slab holds this frame before any peer reads it
+            # stream-ordered barrier (every slab holds this frame before any peer reads it) that also merges the
+            # brick flags: a rank flags only the bricks ITS slices touch; the raycaster needs the union
+            if self._bricks is not None:
+                self.dist.all_reduce(self._bricks, op=self.dist.ReduceOp.MAX)
+            else:
+                self.dist.all_reduce(self._token)
         return done
 
     def raycasting(self, k, mu: float, frame: int) -> bool:

@@ -29,7 +29,8 @@ def _worker(rank, world, port, mode, q):
         T0 = (np.array(synth.INIT_POS_FACTOR, np.float32) * np.float32(4.8)).astype(np.float32)
         depth, _ = synth.make_sequence(N_FRAMES)
         out = {"poses": [], "flags": []}
-        with sharded.ShardedKfusion((640, 480), VRES, 4.8, T0, (10, 5, 4), rank=rank, world=world, device=rank, icp_mode=mode) as s:
+        with sharded.ShardedKfusion((640, 480), VRES, 4.8, T0, (10, 5, 4), rank=rank, world=world, device=rank, icp_mode=mode,
+                                    balance_k=K if mode == "replicated" else None) as s:   # load-aware and even slabs
             for f in range(N_FRAMES):
                 s.preprocessing(depth[f])
                 tr = s.tracking(K, 1e-5, 1, f)

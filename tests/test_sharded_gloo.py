@@ -29,6 +29,18 @@ def test_partitions():
         sharded.row_bands(480, 7)
     with pytest.raises(ValueError):
         sharded.slab_bounds(3, 4)
+    # load-aware boundaries: contiguous cover, aligned, heavier regions get thinner slabs
+    w = np.concatenate([np.zeros(64), np.linspace(1, 50, 192)])
+    for world in (2, 4, 8):
+        sl = sharded.slab_bounds(256, world, w, align=8)
+        assert sl[0][0] == 0 and sl[-1][1] == 256 and len(sl) == world
+        assert all(a[1] == b[0] for a, b in zip(sl, sl[1:])) and all(z0 % 8 == 0 and z1 > z0 for z0, z1 in sl)
+        assert sl[0][1] - sl[0][0] > sl[-1][1] - sl[-1][0]
+    assert sharded.slab_bounds(64, 4, np.ones(64), align=8)[0][0] == 0
+    from slambench_b200 import synth
+    K = np.array(synth.K_DEFAULT, np.float32)
+    fw = sharded.frustum_slice_weights(64, 4.8, kf.identity_pose([2.4, 2.4, 1.2]), K, (640, 480), far=3.2)
+    assert fw[:16].sum() == 0 and fw[20:56].min() > 0 and np.all(np.diff(fw[20:56]) >= 0)    # behind the camera: nothing; then growing
 
 
 def synthetic_track_data(level):
@@ -57,7 +69,9 @@ class FakeLocal:
     def __init__(self, device, slab, flags):
         self.slab, self.rows = slab, None
         self.lib = kf.load_library()
-        self.t = {kf.BUF_VERTEX: torch.zeros(H, W, 3), kf.BUF_NORMAL: torch.zeros(H, W, 3), kf.BUF_REDUCTION_DEV: torch.zeros(32)}
+        self.t = {kf.BUF_VERTEX: torch.zeros(H, W, 3), kf.BUF_NORMAL: torch.zeros(H, W, 3), kf.BUF_REDUCTION_DEV: torch.zeros(32),
+                  kf.BUF_BRICKFLAGS: torch.zeros(2, 2, 2, dtype=torch.uint8)}
+        assert flags & kf.FLAG_BRICKS_MERGED
         self.pose = np.eye(4, dtype=np.float32)
         self.host = {}
         self.calls = []
@@ -122,6 +136,7 @@ class FakeLocal:
 
     def integration(self, k, rate, mu, frame):
         self.calls.append("integrate")
+        self.t[kf.BUF_BRICKFLAGS].view(-1)[self.rank] = 1      # each rank flags what its own slices touch
         return True
 
     def raycasting(self, k, mu, frame):
@@ -178,6 +193,7 @@ def _worker(rank, world, port, q):
         assert np.array_equal(loc.host[kf.BUF_REDUCTION], last)
         assert s.tracking(np.zeros(4, np.float32), 1e-5, 2, frame=7) is False       # frame % tracking_rate gate
         assert s.integration(None, 1, 0.1, 7) is True
+        assert loc.t[kf.BUF_BRICKFLAGS].view(-1)[:3].tolist() == [1, 1, 0], "brick flags must be the union over ranks"
         q.put((rank, pose.copy(), bool(tracked)))
     finally:
         dist.destroy_process_group()
