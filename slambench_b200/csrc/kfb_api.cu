@@ -94,6 +94,9 @@ struct kfb_ctx {
 	bool brick_off;
 	unsigned int* d_queue_ctr;  // 2 slots x {count, head}
 	int int_grid;               // persistent CTAs of k_integrate_run
+	int ray_grid;               // persistent CTAs of k_raycast
+	unsigned int* d_tile_ctr;   // two alternating tile counters
+	uint64_t ray_launches;
 	uint64_t int_launches;
 	int dmax_slot;              // slot holding the max of the CURRENT floatDepth, -1 = unknown
 	uint64_t preprocess_count;
@@ -293,6 +296,16 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	c->dmax_slot = -1; c->preprocess_count = 0;
 	{ const char* e = getenv("KFB_INT_ZCHUNK"); c->int_zchunk = e ? (uint32_t) atoi(e) : 0; }
 	c->d_queue = nullptr; c->queue_cap = 0; c->int_launches = 0;
+	c->ray_launches = 0;
+	CK(cudaMalloc(&c->d_tile_ctr, 2 * sizeof(unsigned int)));
+	CK(cudaMemsetAsync(c->d_tile_ctr, 0, 2 * sizeof(unsigned int), c->stream));
+	{
+		int per_sm = 0, sms = 0;
+		CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast, RCK_BX * RCK_BY, 0));
+		if (per_sm < 1) per_sm = 1;
+		c->ray_grid = sms * per_sm;
+	}
 	CK(cudaMalloc(&c->d_queue_ctr, 4 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_queue_ctr, 0, 4 * sizeof(unsigned int), c->stream));
 	{
@@ -337,7 +350,7 @@ int kfb_destroy(kfb_ctx* c) {
 	if (c->brick.flag) cudaFree(c->brick.flag);
 	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_floatDepth);
 	for (int l = 0; l < c->levels; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
-	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax); cudaFree(c->d_queue_ctr); if (c->d_queue) cudaFree(c->d_queue);
+	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax); cudaFree(c->d_queue_ctr); cudaFree(c->d_tile_ctr); if (c->d_queue) cudaFree(c->d_queue);
 	if (c->d_icp_prof) {
 		unsigned long long h[8];
 		if (cudaMemcpy(h, c->d_icp_prof, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[4])
@@ -703,8 +716,9 @@ static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP
 	p.row0 = c->band0; p.row1 = c->band1;
 	p.view = toMat(view);
 	p.nearPlane = nearP; p.farPlane = farP; p.step = step; p.largestep = largestep;
-	dim3 block(RCK_BX * RCK_BY), grid((p.w + RCK_BX - 1) / RCK_BX, (p.row1 - p.row0 + RCK_BY - 1) / RCK_BY);
-	k_raycast<<<grid, block, 0, c->stream>>>(p);
+	const int slot = (int) (c->ray_launches++ & 1);
+	p.tile_next = c->d_tile_ctr + slot; p.tile_reset = c->d_tile_ctr + (slot ^ 1);
+	k_raycast<<<c->ray_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p);
 	LAUNCHED(c);
 	CK(cudaGetLastError());
 	return 0;

@@ -972,11 +972,20 @@ __device__ __forceinline__ const short2* vol_plane(const VolView& v, int z) {   
 	return v.slab_ptr[s] + (size_t) ((uint32_t) z - v.slab_z[s]) * v.sx * v.sy;
 }
 
+__device__ __forceinline__ float div_cell(float a, float d, float rd, int ok) {
+	if (ok) {
+		const float q = a * rd;
+		return __fmaf_rn(__fmaf_rn(-d, q, a), rd, q);
+	}
+	return a / d;
+}
 struct VolCell { int bx, by, bz; float fx, fy, fz; };
 __device__ __forceinline__ VolCell vol_cell(const VolView& v, float3 pos) {   // commons.h:192-197: scaled position -> base voxel + fraction
-	const float spx = div_const(pos.x * (float) v.sx, v.dx, v.rdx, v.fastdiv) - 0.5f;
-	const float spy = div_const(pos.y * (float) v.sy, v.dy, v.rdy, v.fastdiv) - 0.5f;
-	const float spz = div_const(pos.z * (float) v.sz, v.dz, v.rdz, v.fastdiv) - 0.5f;
+	// div_cell: the range guard of div_const is not needed here — a zero / denormal numerator gives 0 - 0.5 = -0.5 on
+	// both paths, and a non-finite position is outside anything the reference can sample
+	const float spx = div_cell(pos.x * (float) v.sx, v.dx, v.rdx, v.fastdiv) - 0.5f;
+	const float spy = div_cell(pos.y * (float) v.sy, v.dy, v.rdy, v.fastdiv) - 0.5f;
+	const float spz = div_cell(pos.z * (float) v.sz, v.dz, v.rdz, v.fastdiv) - 0.5f;
 	const float flx = floorf(spx), fly = floorf(spy), flz = floorf(spz);
 	VolCell c;
 	// base is in [-1, N-1] for every position the reference samples (inside the volume box); clamping the base itself
@@ -990,7 +999,7 @@ __device__ __forceinline__ VolCell vol_cell(const VolView& v, float3 pos) {   //
 __device__ __forceinline__ bool vol_cell_free(const VolView& v, const VolCell& c) {
 	if (!v.brick) return false;
 	const uint32_t bx = (uint32_t) kmaxi(c.bx, 0) >> BRICK_SHIFT, by = (uint32_t) kmaxi(c.by, 0) >> BRICK_SHIFT, bz = (uint32_t) kmaxi(c.bz, 0) >> BRICK_SHIFT;
-	return __ldg(v.brick + ((size_t) bz * v.bny + by) * v.bnx + bx) == 0;
+	return __ldg(v.brick + ((bz * v.bny + by) * v.bnx + bx)) == 0;   // < 2^32 bricks
 }
 __device__ __forceinline__ float vol_interp_cell(const VolView& v, const VolCell& c) {  // commons.h:198-212
 	const int bx = c.bx, by = c.by, bz = c.bz;
@@ -1095,6 +1104,8 @@ struct RaycastParams {
 	uint32_t row0, row1;            // rows handled by this context (multi-GPU: a band of pixels)
 	Mat4 view;
 	float nearPlane, farPlane, step, largestep;
+	unsigned int* tile_next;        // dynamic tile counter of this launch; tile_reset is zeroed for the next one
+	unsigned int* tile_reset;
 };
 
 #define RC_BX 16
@@ -1102,22 +1113,32 @@ struct RaycastParams {
 // CTA = 32x8 pixels as 8 warps of 8x4 pixels: neighbouring rays walk neighbouring voxels (L1 reuse of the taps)
 #define RCK_BX 32
 #define RCK_BY 4
+// Persistent warps pull 8x4-pixel tiles from a counter: rays differ a lot in length (near objects vs the far wall),
+// and with a static grid the last wave leaves most SMs idle.
 __global__ void __launch_bounds__(RCK_BX* RCK_BY) k_raycast(RaycastParams p) {
-	const uint32_t tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-	const uint32_t x = blockIdx.x * RCK_BX + (wid & 3) * 8 + (lane & 7);
-	const uint32_t y = p.row0 + blockIdx.y * RCK_BY + (wid >> 2) * 4 + (lane >> 3);
-	if (x >= p.w || y >= p.row1) return;
-	const size_t idx = (size_t) x + (size_t) y * p.w;
-	float hw;
-	const float3 hit = raycast_one(p.vol, x, y, p.view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw);
-	if (hw > 0.0f) {
-		st3(p.vertex, idx, hit);
-		const float3 surfNorm = vol_grad(p.vol, hit);
-		if (klength(surfNorm) == 0) p.normal[3 * idx] = KFB_INVALID;  // only .x (:745)
-		else st3(p.normal, idx, knormalize(surfNorm));
-	} else {
-		st3(p.vertex, idx, f3(0, 0, 0));
-		st3(p.normal, idx, f3(KFB_INVALID, 0, 0));
+	const uint32_t lane = threadIdx.x & 31;
+	if (blockIdx.x == 0 && threadIdx.x == 0) *p.tile_reset = 0u;
+	const uint32_t tiles_x = (p.w + 7) / 8, tiles_y = (p.row1 - p.row0 + 3) / 4, tiles = tiles_x * tiles_y;
+	for (;;) {
+		uint32_t t = 0;
+		if (lane == 0) t = atomicAdd(p.tile_next, 1u);
+		t = __shfl_sync(0xffffffffu, t, 0);
+		if (t >= tiles) break;
+		const uint32_t x = (t % tiles_x) * 8 + (lane & 7);
+		const uint32_t y = p.row0 + (t / tiles_x) * 4 + (lane >> 3);
+		if (x >= p.w || y >= p.row1) continue;
+		const size_t idx = (size_t) x + (size_t) y * p.w;
+		float hw;
+		const float3 hit = raycast_one(p.vol, x, y, p.view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw);
+		if (hw > 0.0f) {
+			st3(p.vertex, idx, hit);
+			const float3 surfNorm = vol_grad(p.vol, hit);
+			if (klength(surfNorm) == 0) p.normal[3 * idx] = KFB_INVALID;  // only .x (:745)
+			else st3(p.normal, idx, knormalize(surfNorm));
+		} else {
+			st3(p.vertex, idx, f3(0, 0, 0));
+			st3(p.normal, idx, f3(KFB_INVALID, 0, 0));
+		}
 	}
 }
 
