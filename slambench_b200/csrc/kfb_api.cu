@@ -283,9 +283,10 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 		int coop = 0, per_sm = 0, sms = 0;
 		CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
 		CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
-		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp, TR_THREADS, 0));
+		CK(cudaFuncSetAttribute(k_icp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) ICP_SMEM_BYTES));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp, ICP_THREADS, ICP_SMEM_BYTES));
 		if (!coop || per_sm < 1) return set_err(KFB_E_CUDA, "device cannot co-schedule the ICP kernel (cooperative launch %d, CTAs/SM %d)", coop, per_sm);
-		if (per_sm > 2) per_sm = 2;
+		if (per_sm > 512 / ICP_THREADS) per_sm = 512 / ICP_THREADS;
 		c->icp_grid = sms * per_sm;
 		if (c->icp_grid > TR_MAX_BLOCKS) c->icp_grid = TR_MAX_BLOCKS;
 	}
@@ -601,7 +602,7 @@ int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracki
 			p.status = (c->cfg.flags & KFB_FLAG_TRACK_STATUS) ? c->d_status : nullptr;
 			c->h_out32[33] = 0.f;
 			void* args[] = { &p };
-			CK(cudaLaunchCooperativeKernel((const void*) k_icp, dim3(c->icp_grid), dim3(TR_THREADS), args, 0, c->stream));
+			CK(cudaLaunchCooperativeKernel((const void*) k_icp, dim3(c->icp_grid), dim3(ICP_THREADS), args, ICP_SMEM_BYTES, c->stream));
 			LAUNCHED(c);
 			rc = wait_seq(c, p.seq);
 			if (rc) return rc;

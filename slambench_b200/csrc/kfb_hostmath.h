@@ -140,7 +140,11 @@ KFB_HM int hm_solve6_chol(double* x6, const float* vals27) {
 #pragma unroll
 		for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
 		if (!(s > 0)) return 0;
+#if defined(__CUDA_ARCH__)
+		const double inv = rsqrt(s), d = s * inv;   // one special-function step on the serial path instead of sqrt + divide
+#else
 		const double d = sqrt(s), inv = 1.0 / d;
+#endif
 		L[j][j] = d; M[j][j] = inv;
 #pragma unroll
 		for (int i = j + 1; i < 6; ++i) {

@@ -70,7 +70,8 @@ __global__ void __launch_bounds__(PP_BX* PP_BY) k_mm2m_bilateral(const uint16_t*
 			const float curPix = tile[threadIdx.y + PP_R + j][threadIdx.x + PP_R + i];
 			if (curPix > 0) {
 				const float mod = ksq(curPix - center);
-				const float factor = gs.g[i + PP_R] * gs.g[j + PP_R] * kfb_expf_nonpos(-mod / e_d_squared_2);
+				// expf(-0) == 1 exactly: equal depths (flat, fronto-parallel surfaces; the centre tap) skip the fp64 routine
+				const float factor = gs.g[i + PP_R] * gs.g[j + PP_R] * (mod == 0.f ? 1.0f : kfb_expf_nonpos(-mod / e_d_squared_2));
 				t += factor * curPix;
 				sum += factor;
 			}
@@ -464,9 +465,16 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 	return t;
 }
 
-__global__ void __launch_bounds__(TR_THREADS, 2) k_icp(IcpParams p) {
-	__shared__ double sm[TR_THREADS / 32][32];
-	__shared__ float xs[32][TR_THREADS];   // 32 KB: per-thread sums, transposed
+#ifndef ICP_THREADS
+#define ICP_THREADS 512   // one CTA per SM: half the partial rows for the last CTA to sum (measured 12.0 -> 11.3 us / iteration)
+#endif
+#define ICP_NW (ICP_THREADS / 32)          // warps per CTA
+#define ICP_VPW (32 / ICP_NW)              // reduction outputs summed by each warp
+#define ICP_SMEM_BYTES (32 * ICP_THREADS * sizeof(float))
+__global__ void __launch_bounds__(ICP_THREADS, 512 / ICP_THREADS) k_icp(IcpParams p) {
+	__shared__ double sm[ICP_NW][32];
+	extern __shared__ float xs_raw[];       // [32][ICP_THREADS]: per-thread sums, transposed (dynamic: 64 KB at 512 threads)
+	float (*xs)[ICP_THREADS] = reinterpret_cast<float (*)[ICP_THREADS]>(xs_raw);
 	__shared__ float red32[32];
 	__shared__ Mat4 Tsh;
 	__shared__ int flag_sh;   // 1: this CTA arrived last; 2: barrier time-out
@@ -485,14 +493,14 @@ __global__ void __launch_bounds__(TR_THREADS, 2) k_icp(IcpParams p) {
 			const Mat4 T = Tsh;
 			TrackAcc acc;
 			acc.clear();
-			for (uint32_t i = blockIdx.x * TR_THREADS + threadIdx.x; i < npx; i += 2 * gridDim.x * TR_THREADS) {
-				const uint32_t pix[2] = { i, i + gridDim.x * TR_THREADS };
+			for (uint32_t i = blockIdx.x * ICP_THREADS + threadIdx.x; i < npx; i += 2 * gridDim.x * ICP_THREADS) {
+				const uint32_t pix[2] = { i, i + gridDim.x * ICP_THREADS };
 				const bool on[2] = { true, pix[1] < npx };
 				track_pixels<2>(acc, p.inV[level], p.inN[level], p.refV, p.refN, w, p.rw, p.rh, pix, on, T, V, p.dist_threshold,
 						p.normal_threshold, p.status);
 			}
 			// thread -> CTA through shared memory, fp64, fixed order: value i of thread t sits at xs[i][t]; warp w
-			// sums values 4w..4w+3 (lane l adds threads l, l+32, .. in order, then a 5-step butterfly)
+			// sums values ICP_VPW*w .. (lane l adds threads l, l+32, .. in order, then a 5-step butterfly)
 			__syncthreads();
 #pragma unroll
 			for (int i = 0; i < 28; ++i) xs[i][threadIdx.x] = acc.s[i];
@@ -500,11 +508,11 @@ __global__ void __launch_bounds__(TR_THREADS, 2) k_icp(IcpParams p) {
 			xs[30][threadIdx.x] = (float) acc.c30; xs[31][threadIdx.x] = (float) acc.c31;
 			__syncthreads();
 #pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				const int i = wid * 4 + q;
+			for (int q = 0; q < ICP_VPW; ++q) {
+				const int i = wid * ICP_VPW + q;
 				double v = 0;
 #pragma unroll
-				for (int k = 0; k < TR_THREADS / 32; ++k) v += (double) xs[i][lane + 32 * k];
+				for (int k = 0; k < ICP_NW; ++k) v += (double) xs[i][lane + 32 * k];
 				v = warp_sum(v);
 				if (lane == 0) __stcg(p.partials + (size_t) blockIdx.x * 32 + i, v);
 			}
@@ -516,24 +524,24 @@ __global__ void __launch_bounds__(TR_THREADS, 2) k_icp(IcpParams p) {
 			__syncthreads();
 			if (flag_sh) {
 				// last CTA: every partial row is visible (each writer fenced before its ticket).  Warp w sums rows
-				// w, w+8, ... with four independent accumulators (loads overlap), always in the same order.
+				// w, w + ICP_NW, ... with eight independent accumulators (loads overlap), always in the same order.
 				__threadfence();
 				double va[8];
 #pragma unroll
 				for (int j = 0; j < 8; ++j) va[j] = 0;
 				uint32_t b = wid;
 				const double* part = p.partials + lane;
-				for (; b + 56 < gridDim.x; b += 64) {
+				for (; b + 7 * ICP_NW < gridDim.x; b += 8 * ICP_NW) {
 					double a[8];
 #pragma unroll
-					for (int j = 0; j < 8; ++j) a[j] = __ldcg(part + (size_t) (b + 8 * j) * 32);
+					for (int j = 0; j < 8; ++j) a[j] = __ldcg(part + (size_t) (b + ICP_NW * j) * 32);
 #pragma unroll
 					for (int j = 0; j < 8; ++j) va[j] += a[j];
 				}
 				{
 					double a[8];
 #pragma unroll
-					for (int j = 0; j < 8; ++j) a[j] = (b + 8 * j < gridDim.x) ? __ldcg(part + (size_t) (b + 8 * j) * 32) : 0.0;
+					for (int j = 0; j < 8; ++j) a[j] = (b + ICP_NW * j < gridDim.x) ? __ldcg(part + (size_t) (b + ICP_NW * j) * 32) : 0.0;
 #pragma unroll
 					for (int j = 0; j < 8; ++j) va[j] += a[j];
 				}
@@ -542,7 +550,7 @@ __global__ void __launch_bounds__(TR_THREADS, 2) k_icp(IcpParams p) {
 				if (wid == 0) {
 					double t = 0;
 #pragma unroll
-					for (int k = 0; k < TR_THREADS / 32; ++k) t += sm[k][lane];
+					for (int k = 0; k < ICP_NW; ++k) t += sm[k][lane];
 					const float r = (float) t;
 					red32[lane] = r;
 					p.out32[lane] = r;            // device copy; mirrored to the host once, at the end
