@@ -120,52 +120,56 @@ KFB_HM void hm_solve6(double* x6, const float* vals27) {
 // => GR_SVD::backsub keeps them all => x = C^-1 b), a Cholesky solve in double gives the same x to
 // ~cond * 1e-16.  Returns 0 (caller falls back to hm_solve6) when the certificate fails: not
 // positive definite (start-up frames: C == 0), NaN, or possibly ill-conditioned.
+#define KFB_TRI(i, j) ((i) * ((i) + 1) / 2 + (j))   // packed lower triangle, j <= i
 KFB_HM int hm_solve6_chol(double* x6, const float* vals27) {
-	double b[6], C[6][6], L[6][6], M[6][6];
+	// packed lower triangles only (21 + 21 doubles) so that the whole solve stays in registers on the device
+	double b[6], L[21], M[21];
 #pragma unroll
 	for (int i = 0; i < 6; ++i) b[i] = vals27[i];
 	{
+		// vals27[6..26] is the UPPER triangle row by row (commons.h:385-392): C[r][c], c >= r  ->  L slot (c, r)
 		int idx = 6;
 #pragma unroll
 		for (int r = 0; r < 6; ++r)
 #pragma unroll
-			for (int c = r; c < 6; ++c) { C[r][c] = vals27[idx++]; C[c][r] = C[r][c]; }
+			for (int c = r; c < 6; ++c) L[KFB_TRI(c, r)] = vals27[idx++];
 	}
 	double trC = 0;
 #pragma unroll
-	for (int i = 0; i < 6; ++i) trC += C[i][i];
+	for (int i = 0; i < 6; ++i) trC += L[KFB_TRI(i, i)];
+	// in-place Cholesky, column by column; M's diagonal takes the reciprocal pivots
 #pragma unroll
 	for (int j = 0; j < 6; ++j) {
-		double s = C[j][j];
+		double s = L[KFB_TRI(j, j)];
 #pragma unroll
-		for (int k = 0; k < j; ++k) s -= L[j][k] * L[j][k];
+		for (int k = 0; k < j; ++k) s -= L[KFB_TRI(j, k)] * L[KFB_TRI(j, k)];
 		if (!(s > 0)) return 0;
 #if defined(__CUDA_ARCH__)
 		const double inv = rsqrt(s), d = s * inv;   // one special-function step on the serial path instead of sqrt + divide
 #else
 		const double d = sqrt(s), inv = 1.0 / d;
 #endif
-		L[j][j] = d; M[j][j] = inv;
+		L[KFB_TRI(j, j)] = d; M[KFB_TRI(j, j)] = inv;
 #pragma unroll
 		for (int i = j + 1; i < 6; ++i) {
-			double t = C[i][j];
+			double t = L[KFB_TRI(i, j)];
 #pragma unroll
-			for (int k = 0; k < j; ++k) t -= L[i][k] * L[j][k];
-			L[i][j] = t * inv;
+			for (int k = 0; k < j; ++k) t -= L[KFB_TRI(i, k)] * L[KFB_TRI(j, k)];
+			L[KFB_TRI(i, j)] = t * inv;
 		}
 	}
 	// M = L^-1 (lower triangular); trace(C^-1) = ||M||_F^2
 	double trInv = 0;
 #pragma unroll
 	for (int j = 0; j < 6; ++j) {
-		trInv += M[j][j] * M[j][j];   // M[j][j] = 1 / L[j][j] from the factorisation
+		trInv += M[KFB_TRI(j, j)] * M[KFB_TRI(j, j)];
 #pragma unroll
 		for (int i = j + 1; i < 6; ++i) {
 			double t = 0;
 #pragma unroll
-			for (int k = j; k < i; ++k) t -= L[i][k] * M[k][j];
-			M[i][j] = t * M[i][i];
-			trInv += M[i][j] * M[i][j];
+			for (int k = j; k < i; ++k) t -= L[KFB_TRI(i, k)] * M[KFB_TRI(k, j)];
+			M[KFB_TRI(i, j)] = t * M[KFB_TRI(i, i)];
+			trInv += M[KFB_TRI(i, j)] * M[KFB_TRI(i, j)];
 		}
 	}
 	if (!(trC * trInv < 0.99e6)) return 0;
@@ -174,14 +178,14 @@ KFB_HM int hm_solve6_chol(double* x6, const float* vals27) {
 	for (int i = 0; i < 6; ++i) {
 		double t = 0;
 #pragma unroll
-		for (int j = 0; j <= i; ++j) t += M[i][j] * b[j];
+		for (int j = 0; j <= i; ++j) t += M[KFB_TRI(i, j)] * b[j];
 		y[i] = t;
 	}
 #pragma unroll
 	for (int j = 0; j < 6; ++j) {
 		double t = 0;
 #pragma unroll
-		for (int i = j; i < 6; ++i) t += M[i][j] * y[i];
+		for (int i = j; i < 6; ++i) t += M[KFB_TRI(i, j)] * y[i];
 		x6[j] = t;
 	}
 	return 1;
