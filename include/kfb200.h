@@ -30,9 +30,10 @@ extern "C" {
 typedef struct kfb_ctx kfb_ctx;
 
 /* flags for kfb_config.flags */
-#define KFB_FLAG_ICP_HOST_SOLVE 0x1u   /* solve the 6x6 system on the host every ICP iteration (debug/parity aid)   */
+#define KFB_FLAG_ICP_HOST_SOLVE 0x1u   /* one k_track_reduce launch + host 6x6 solve per ICP iteration: the reference's control flow
+                                         verbatim (A/B check); default = one persistent cooperative kernel per frame            */
 #define KFB_FLAG_TRACK_STATUS   0x2u   /* keep the per-pixel ICP status plane that renderTrack visualises           */
-#define KFB_FLAG_NO_GRAPHS      0x4u   /* do not capture per-frame work into CUDA graphs                              */
+#define KFB_FLAG_RESERVED_4     0x4u   /* reserved (was: CUDA-graph switch); ignored                                   */
 #define KFB_FLAG_INTEGRATE_NO_CULL 0x8u /* integrate visits every voxel with the reference's full expression (A/B check) */
 #define KFB_FLAG_RAYCAST_NO_SKIP 0x10u  /* raycast evaluates every sample (no brick flags) (A/B check)                    */
 #define KFB_FLAG_BRICKS_MERGED 0x20u    /* z-slab mode: the caller merges (element-wise max over ranks) KFB_BUF_BRICKFLAGS between

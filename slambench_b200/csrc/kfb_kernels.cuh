@@ -662,7 +662,9 @@ __global__ void __launch_bounds__(256) k_brick_rebuild(BrickMap b, const short2*
 // The kernel is launched on the slab [z_begin, z_end) this context owns; `vol` points at the
 // slab's first voxel.  N_upd (voxels actually updated) is counted exactly.
 // ------------------------------------------------------------------------------------------
-#define INT_U 8
+#ifndef INT_U
+#define INT_U 8   // slices per batch (must divide 8: a batch never straddles a brick layer)
+#endif
 struct IntegrateParams {
 	short2* vol;
 	uint32_t sx, sy, sz;       // full volume resolution
@@ -896,7 +898,7 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run(Integr
 			// Batches start at multiples of 8 when the flags are maintained (the plan pass aligns za), so a batch is
 			// one brick layer bz = z / 8 plus, through its first slice, the halo of layer bz - 1.
 			if (p.brick.flag) {
-				const unsigned int m_any = __ballot_sync(0xffffffffu, low != 0u), m_0 = __ballot_sync(0xffffffffu, low & 1u);
+				const unsigned int m_any = __ballot_sync(0xffffffffu, low != 0u), m_0 = ((z & 7) == 0) ? __ballot_sync(0xffffffffu, low & 1u) : 0u;
 				if (m_any && lane < 5) {
 					const int j = (int) lane - 1;   // x-brick relative to the warp's first brick: -1 (halo of the previous tile) .. 3
 					unsigned int any = 0, first = 0;

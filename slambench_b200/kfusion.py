@@ -19,7 +19,6 @@ from . import build as _build
 KFB_MAX_LEVELS = 8
 FLAG_ICP_HOST_SOLVE = 0x1
 FLAG_TRACK_STATUS = 0x2
-FLAG_NO_GRAPHS = 0x4
 FLAG_INTEGRATE_NO_CULL = 0x8
 FLAG_RAYCAST_NO_SKIP = 0x10
 FLAG_BRICKS_MERGED = 0x20
@@ -195,10 +194,15 @@ class Kfusion:
         return False  # the reference always returns false (cpp/kernels.cpp:975-984)
 
     def computeFrame(self, inputDepth, inputSize, k, integration_rate, tracking_rate, icp_threshold, mu, frame):
-        self.preprocessing(inputDepth, inputSize)
-        self._tracked = self.tracking(k, icp_threshold, tracking_rate, frame)
-        self._integrated = self.integration(k, integration_rate, mu, frame)
-        self.raycasting(k, mu, frame)
+        """Kfusion::computeFrame (cpp/kernels.cpp:1048-1055) through the single C-ABI entry point."""
+        d = inputDepth if (inputDepth.dtype == np.uint16 and inputDepth.flags.c_contiguous) else np.ascontiguousarray(inputDepth, np.uint16)
+        h, w = d.shape if inputSize is None else (inputSize[1], inputSize[0])
+        self._keep = d
+        tr, it = C.c_int(0), C.c_int(0)
+        self._check(self.lib.kfb_compute_frame(self._h, _p(d), C.c_uint32(w), C.c_uint32(h), _p(_f32(k, 4)), C.c_uint32(integration_rate),
+                                               C.c_uint32(tracking_rate), C.c_float(icp_threshold), C.c_float(mu), C.c_uint32(frame),
+                                               C.byref(tr), C.byref(it)))
+        self._tracked, self._integrated = bool(tr.value), bool(it.value)
 
     def getTracked(self) -> bool:
         return self._tracked

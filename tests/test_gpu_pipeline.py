@@ -287,3 +287,16 @@ def test_odd_configurations(port, seq16, res, dim, csize, pyr, pose_tol):
     d = np.abs(a[2].astype(np.int32) - vol_c.astype(np.int32)).max(-1)
     assert (d <= 1).mean() > 0.99
     assert ((a[4][..., 0] != -2) == (nrm_c[..., 0] != -2)).mean() > 0.99
+
+
+def test_compute_frame_entry_point(seq16):
+    """kfb_compute_frame == preprocessing + tracking + integration + raycasting (cpp/kernels.cpp:1048-1055)."""
+    depth, _ = seq16
+    n = 8
+    pa, ta, ia = run_gpu_pipeline(depth, n, 96)
+    with kf.Kfusion((640, 480), 96, 4.8, T0, (10, 5, 4)) as g:
+        for f in range(n):
+            g.computeFrame(depth[f], None, K, 1, 1, 1e-5, 0.1, f)
+            assert (g.getTracked(), g.getIntegrated()) == (ta[f], ia[f])
+            assert np.array_equal(g.getPose(), pa[f])
+        assert np.array_equal(g.getPosition(), g.getPose()[:3, 3] - T0)
