@@ -362,7 +362,24 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
     T0 = (np.array(synth.INIT_POS_FACTOR, np.float32) * np.float32(VOLUME_DIM)).astype(np.float32)
     n = args.warmup + args.steps
     n_diag = 6                                    # extra frames for the per-stage breakdown (after the timed region)
-    depth_np, gt = synth.make_sequence(n + n_diag, long_run=False if n + n_diag <= 400 else None)
+    if n + n_diag <= 200:
+        depth_np, gt = synth.make_sequence(n + n_diag, long_run=False)
+    else:
+        # long runs (configs[4]: 1000 frames): every rank renders the frames f == rank (mod world) and the ranks
+        # all-gather them over NCCL — the sequence is identical on every rank and to synth.make_sequence()
+        long_run = n + n_diag > 400
+        total = n + n_diag
+        mine = list(range(rank, total, world))
+        per = (total + world - 1) // world
+        loc = torch.zeros((per, H_IMG, W_IMG), dtype=torch.int16, device=f"cuda:{local_rank}")
+        for i, f in enumerate(mine):
+            img = synth.render_depth_mm(synth.trajectory_pose(f, 0, long_run))
+            loc[i] = torch.from_numpy(img.view(np.int16)).to(loc.device)
+        allf = torch.empty((world, per, H_IMG, W_IMG), dtype=torch.int16, device=loc.device)
+        dist.all_gather_into_tensor(allf.view(world * per, H_IMG, W_IMG), loc)
+        depth_np = allf.permute(1, 0, 2, 3).reshape(world * per, H_IMG, W_IMG)[:total].contiguous().cpu().numpy().view(np.uint16)
+        gt = np.stack([synth.trajectory_pose(f, 0, long_run) for f in range(total)])
+        del loc, allf
     host = torch.from_numpy(depth_np).pin_memory()
     depth_np = host.numpy()
     with sharded.ShardedKfusion((W_IMG, H_IMG), args.volume, VOLUME_DIM, T0, PYRAMID, rank=rank, world=world, device=local_rank,

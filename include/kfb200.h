@@ -79,7 +79,8 @@ enum kfb_buffer {
 	KFB_BUF_GAUSSIAN = 11,    /* float[5]                                                 `gaussian`         */
 	KFB_BUF_INPUTDEPTH = 12,  /* uint16[in_w*in_h] device copy of the last sensor frame                      */
 	KFB_BUF_REDUCTION_DEV = 13, /* float[32] DEVICE copy of the last track+reduce result (multi-GPU all-reduce operand) */
-	KFB_BUF_BRICKFLAGS = 14   /* uint8[ceil(N/8)^3] brick flags of the WHOLE volume (see KFB_FLAG_BRICKS_MERGED)            */
+	KFB_BUF_BRICKFLAGS = 14,  /* uint8[ceil(N/8)^3] brick flags of the WHOLE volume (see KFB_FLAG_BRICKS_MERGED)            */
+	KFB_BUF_RAYTILECOST = 15  /* uint32[ceil(h/4)][ceil(w/8)] SM cycles per raycast tile, last launch (env KFB_RAY_TILECOST=1)   */
 };
 
 int kfb_abi_version(void);

@@ -96,6 +96,7 @@ struct kfb_ctx {
 	int int_grid;               // persistent CTAs of k_integrate_run
 	int ray_grid;               // persistent CTAs of k_raycast
 	unsigned int* d_tile_ctr;   // two alternating tile counters
+	unsigned int* d_tile_cost;  // KFB_RAY_TILECOST=1: cycles per raycast tile of the last launch (diagnostics)
 	uint64_t ray_launches;
 	uint64_t int_launches;
 	int dmax_slot;              // slot holding the max of the CURRENT floatDepth, -1 = unknown
@@ -298,6 +299,8 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	{ const char* e = getenv("KFB_INT_ZCHUNK"); c->int_zchunk = e ? (uint32_t) atoi(e) : 0; }
 	c->d_queue = nullptr; c->queue_cap = 0; c->int_launches = 0;
 	c->ray_launches = 0;
+	c->d_tile_cost = nullptr;
+	if (getenv("KFB_RAY_TILECOST")) CK(cudaMalloc(&c->d_tile_cost, (size_t) ((c->cw + 7) / 8) * ((c->ch + 3) / 4) * sizeof(unsigned int)));
 	CK(cudaMalloc(&c->d_tile_ctr, 2 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_tile_ctr, 0, 2 * sizeof(unsigned int), c->stream));
 	{
@@ -351,7 +354,7 @@ int kfb_destroy(kfb_ctx* c) {
 	if (c->brick.flag) cudaFree(c->brick.flag);
 	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_floatDepth);
 	for (int l = 0; l < c->levels; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
-	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax); cudaFree(c->d_queue_ctr); cudaFree(c->d_tile_ctr); if (c->d_queue) cudaFree(c->d_queue);
+	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax); cudaFree(c->d_queue_ctr); cudaFree(c->d_tile_ctr); if (c->d_tile_cost) cudaFree(c->d_tile_cost); if (c->d_queue) cudaFree(c->d_queue);
 	if (c->d_icp_prof) {
 		unsigned long long h[8];
 		if (cudaMemcpy(h, c->d_icp_prof, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[4])
@@ -649,8 +652,10 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	// pass 1 cuts every warp-column's visited interval into pieces of `zchunk` slices; pass 2 is persistent
 	// short pieces keep every warp's serial chain short (measured: 256^3 best at 16-32, 512^3 at 64)
 	{
-		uint32_t zc = ((c->z1 - c->z0) / 8) & ~7u;   // a multiple of INT_U so a warp can continue into the next piece
-		zc = zc < 16 ? 16 : (zc > 64 ? 64 : zc);
+		const uint32_t nz = c->z1 - c->z0;
+		uint32_t zc = (nz / 8) & ~7u;   // a multiple of INT_U so a warp can continue into the next piece
+		const uint32_t zc_max = nz <= 512 ? 32u : 64u;   // measured: 512 slices 159 us at 24-32 vs 166 us at 64 (flat below)
+		zc = zc < 16 ? 16 : (zc > zc_max ? zc_max : zc);
 		p.zchunk = c->int_zchunk ? c->int_zchunk : zc;
 	}
 	const int qslot = (int) (c->int_launches++ & 1);   // never reset: the slots alternate strictly
@@ -712,6 +717,7 @@ int kfb_integrate(kfb_ctx* c, const float k[4], uint32_t integration_rate, float
 static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP, float step, float largestep) {
 	RaycastParams p;
 	p.vol = c->view_all;
+	p.tile_cost = c->d_tile_cost;
 	p.vertex = c->d_vertex; p.normal = c->d_normal;
 	p.w = c->cw; p.h = c->ch;
 	p.row0 = c->band0; p.row1 = c->band1;
@@ -870,6 +876,9 @@ static int resolve_buffer(kfb_ctx* c, int which, int level, void** ptr, size_t* 
 	case KFB_BUF_BRICKFLAGS:
 		if (!c->brick.flag) return set_err(KFB_E_STATE, "brick flags are not maintained by this context");
 		*ptr = c->brick.flag; *bytes = (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz; break;
+	case KFB_BUF_RAYTILECOST:
+		if (!c->d_tile_cost) return set_err(KFB_E_STATE, "tile costs are only recorded with KFB_RAY_TILECOST=1");
+		*ptr = c->d_tile_cost; *bytes = (size_t) ((c->cw + 7) / 8) * ((c->ch + 3) / 4) * sizeof(unsigned int); break;
 	default: return set_err(KFB_E_ARG, "unknown buffer %d", which);
 	}
 	return 0;

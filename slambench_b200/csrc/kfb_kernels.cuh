@@ -1108,6 +1108,7 @@ __device__ __forceinline__ float3 raycast_one(const VolView& v, uint32_t px, uin
 }
 
 struct RaycastParams {
+	unsigned int* tile_cost;        // optional: SM cycles each 8x4 tile took (KFB_RAY_TILECOST=1, diagnostics)
 	VolView vol;
 	float* vertex; float* normal;   // packed float3[w*h]
 	uint32_t w, h;
@@ -1136,18 +1137,24 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY) k_raycast(RaycastParams p) {
 		if (t >= tiles) break;
 		const uint32_t x = (t % tiles_x) * 8 + (lane & 7);
 		const uint32_t y = p.row0 + (t / tiles_x) * 4 + (lane >> 3);
-		if (x >= p.w || y >= p.row1) continue;
-		const size_t idx = (size_t) x + (size_t) y * p.w;
-		float hw;
-		const float3 hit = raycast_one(p.vol, x, y, p.view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw);
-		if (hw > 0.0f) {
-			st3(p.vertex, idx, hit);
-			const float3 surfNorm = vol_grad(p.vol, hit);
-			if (klength(surfNorm) == 0) p.normal[3 * idx] = KFB_INVALID;  // only .x (:745)
-			else st3(p.normal, idx, knormalize(surfNorm));
-		} else {
-			st3(p.vertex, idx, f3(0, 0, 0));
-			st3(p.normal, idx, f3(KFB_INVALID, 0, 0));
+		const long long c0 = p.tile_cost ? clock64() : 0;
+		if (x < p.w && y < p.row1) {
+			const size_t idx = (size_t) x + (size_t) y * p.w;
+			float hw;
+			const float3 hit = raycast_one(p.vol, x, y, p.view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw);
+			if (hw > 0.0f) {
+				st3(p.vertex, idx, hit);
+				const float3 surfNorm = vol_grad(p.vol, hit);
+				if (klength(surfNorm) == 0) p.normal[3 * idx] = KFB_INVALID;  // only .x (:745)
+				else st3(p.normal, idx, knormalize(surfNorm));
+			} else {
+				st3(p.vertex, idx, f3(0, 0, 0));
+				st3(p.normal, idx, f3(KFB_INVALID, 0, 0));
+			}
+		}
+		if (p.tile_cost) {   // diagnostics (KFB_RAY_TILECOST=1): how long this tile kept its warp
+			__syncwarp();
+			if (lane == 0) p.tile_cost[t] = (unsigned int) (clock64() - c0);
 		}
 	}
 }

@@ -25,7 +25,7 @@ FLAG_BRICKS_MERGED = 0x20
 
 (BUF_VOLUME, BUF_VERTEX, BUF_NORMAL, BUF_FLOATDEPTH, BUF_SCALEDDEPTH, BUF_INVERTEX, BUF_INNORMAL,
  BUF_REDUCTION, BUF_TRACKSTATUS, BUF_RAYCASTPOSE, BUF_OLDPOSE, BUF_GAUSSIAN, BUF_INPUTDEPTH, BUF_REDUCTION_DEV,
- BUF_BRICKFLAGS) = range(15)
+ BUF_BRICKFLAGS, BUF_RAYTILECOST) = range(16)
 
 # constant_parameters.h:15-23
 E_DELTA, RADIUS, DIST_THRESHOLD, NORMAL_THRESHOLD, TRACK_THRESHOLD = 0.1, 2, 0.1, 0.8, 0.15
@@ -314,6 +314,7 @@ class Kfusion:
             BUF_RAYCASTPOSE: ((4, 4), np.float32), BUF_OLDPOSE: ((4, 4), np.float32), BUF_GAUSSIAN: ((5,), np.float32),
             BUF_REDUCTION_DEV: ((32,), np.float32),
             BUF_BRICKFLAGS: (((vr[2] + 7) // 8, (vr[1] + 7) // 8, (vr[0] + 7) // 8), np.uint8),
+            BUF_RAYTILECOST: (((h + 3) // 4, (w + 7) // 8), np.uint32),
         }[which]
 
     def read(self, which: int, level: int = 0) -> np.ndarray:
