@@ -269,7 +269,7 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
             barrier()
             ms = ev0.elapsed_time(ev1)
             st = g.stats()
-            err = float(np.abs(pose[:3, 3] - gt[n - 1][:3, 3]).max())
+            err = float(np.abs(pose[:3, 3] - synth.expected_pose(gt, n - 1)[:3, 3]).max())
             return dict(ms=ms, wall_ms=wall * 1e3, st=st, tracked=tracked, integrated=integrated, err=err, clocks=ck)
 
     # depth_np must alias the pinned buffer for the e2e arm
@@ -348,6 +348,25 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
         dist.destroy_process_group()
 
 
+def render_sequence_distributed(total: int, rank: int, world: int, torch, dist, device):
+    """Frames f == rank (mod world) rendered here, all frames gathered from the ranks (bytes: NCCL has no int16).
+    Returns (uint16[total, H, W], gt[total, 4, 4]) identical on every rank."""
+    from slambench_b200 import synth
+
+    long_run = total > 400
+    per = (total + world - 1) // world
+    loc = torch.zeros((per, H_IMG, W_IMG * 2), dtype=torch.uint8, device=device)
+    for i, f in enumerate(range(rank, total, world)):
+        img = np.ascontiguousarray(synth.render_depth_mm(synth.trajectory_pose(f, 0, long_run)))
+        loc[i] = torch.from_numpy(img.view(np.uint8).reshape(H_IMG, W_IMG * 2)).to(device)
+    allf = torch.empty((world * per, H_IMG, W_IMG * 2), dtype=torch.uint8, device=device)
+    dist.all_gather_into_tensor(allf, loc)
+    allf = allf.view(world, per, H_IMG, W_IMG * 2).permute(1, 0, 2, 3).reshape(world * per, H_IMG, W_IMG * 2)[:total]
+    depth = np.ascontiguousarray(allf.contiguous().cpu().numpy()).view(np.uint16).reshape(total, H_IMG, W_IMG)
+    gt = np.stack([synth.trajectory_pose(f, 0, long_run) for f in range(total)])
+    return depth, gt
+
+
 def sharded_arm(args, rank: int, world: int, local_rank: int):
     """ONE sequence, the volume cut into z-slabs over the ranks (BASELINE configs[3], [4]): integrate local, raycast
     over NVLink peer slabs + NCCL all-gather, ICP replicated or all-reduced.  Strong scaling: the work is fixed."""
@@ -367,19 +386,7 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
     else:
         # long runs (configs[4]: 1000 frames): every rank renders the frames f == rank (mod world) and the ranks
         # all-gather them over NCCL — the sequence is identical on every rank and to synth.make_sequence()
-        long_run = n + n_diag > 400
-        total = n + n_diag
-        mine = list(range(rank, total, world))
-        per = (total + world - 1) // world
-        loc = torch.zeros((per, H_IMG, W_IMG), dtype=torch.int16, device=f"cuda:{local_rank}")
-        for i, f in enumerate(mine):
-            img = synth.render_depth_mm(synth.trajectory_pose(f, 0, long_run))
-            loc[i] = torch.from_numpy(img.view(np.int16)).to(loc.device)
-        allf = torch.empty((world, per, H_IMG, W_IMG), dtype=torch.int16, device=loc.device)
-        dist.all_gather_into_tensor(allf.view(world * per, H_IMG, W_IMG), loc)
-        depth_np = allf.permute(1, 0, 2, 3).reshape(world * per, H_IMG, W_IMG)[:total].contiguous().cpu().numpy().view(np.uint16)
-        gt = np.stack([synth.trajectory_pose(f, 0, long_run) for f in range(total)])
-        del loc, allf
+        depth_np, gt = render_sequence_distributed(n + n_diag, rank, world, torch, dist, f"cuda:{local_rank}")
     host = torch.from_numpy(depth_np).pin_memory()
     depth_np = host.numpy()
     with sharded.ShardedKfusion((W_IMG, H_IMG), args.volume, VOLUME_DIM, T0, PYRAMID, rank=rank, world=world, device=local_rank,
@@ -420,7 +427,7 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        err = float(np.abs(s.getPose()[:3, 3] - gt[n - 1][:3, 3]).max())
+        err = float(np.abs(s.getPose()[:3, 3] - synth.expected_pose(gt, n - 1)[:3, 3]).max())
         # per-stage breakdown: the same calls with a full sync after each stage (host-visible time, max over ranks)
         stage = np.zeros(4)
         for f in range(n, n + n_diag):

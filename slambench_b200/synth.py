@@ -66,6 +66,15 @@ def trajectory_pose(frame: int, seed: int = 0, long_run: bool = False) -> np.nda
     return T
 
 
+def expected_pose(gt: np.ndarray, frame: int) -> np.ndarray:
+    """Pose a tracker that starts at the reference's initial pose (identity rotation at t0, kernels.h:106-109) should
+    report for `frame`: it builds its model in the frame of ITS first pose, so the ground truth is re-expressed there,
+    P0 * inverse(gt[0]) * gt[frame].  Equal to gt[frame] whenever gt[0] is that initial pose (every short sequence)."""
+    p0 = np.eye(4)
+    p0[:3, 3] = gt[0][:3, 3]
+    return p0 @ np.linalg.inv(gt[0]) @ gt[frame]
+
+
 def _ray_aabb_exit(o, d, lo, hi):
     """Distance to the inside surface of a box that contains `o`."""
     with np.errstate(divide="ignore", invalid="ignore"):
