@@ -308,6 +308,8 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 		CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast, RCK_BX * RCK_BY, 0));
 		if (per_sm < 1) per_sm = 1;
+		const char* e = getenv("KFB_RAY_CTAS_PER_SM");   // tuning: fewer persistent warps = more tiles per warp
+		if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e);
 		c->ray_grid = sms * per_sm;
 	}
 	CK(cudaMalloc(&c->d_queue_ctr, 4 * sizeof(unsigned int)));

@@ -219,3 +219,35 @@ def test_sharded_orchestration_world2_gloo():
     res.sort(key=lambda t: t[0])
     assert np.array_equal(res[0][1], res[1][1]), "every rank must hold the same pose"
     assert res[0][2] == res[1][2]
+
+
+def _render_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench
+
+        depth, gt = bench.render_sequence_distributed(7, rank, world, torch, dist, "cpu")
+        q.put((rank, depth, gt))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_distributed_frame_rendering_world2_gloo():
+    """Long sharded runs render frame f on rank f % world and all-gather the frames (bench.py): every rank must end
+    up with exactly the sequence synth.make_sequence() produces."""
+    from slambench_b200 import synth
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_render_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref, gt = synth.make_sequence(7, long_run=False)
+    for _, depth, g in res:
+        assert depth.dtype == np.uint16 and np.array_equal(depth, ref) and np.allclose(g, gt)

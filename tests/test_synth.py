@@ -41,3 +41,17 @@ def test_long_run_stays_inside_the_room():
     for f in range(0, 1000, 37):
         t = synth.trajectory_pose(f, 0, long_run=True)[:3, 3]
         assert np.all(t > synth.ROOM_LO + 0.3) and np.all(t < synth.ROOM_HI - 0.3)
+
+
+def test_expected_pose_is_ground_truth_in_the_trackers_frame():
+    """A tracker starts at identity rotation (kernels.h:106-109); the 1000-frame trajectory does not, so its ground
+    truth is re-expressed in the tracker's frame.  Short sequences start at the initial pose: nothing changes."""
+    _, gt = synth.make_sequence(8, long_run=False)
+    assert np.allclose(synth.expected_pose(gt, 7), gt[7])
+    gl = np.stack([synth.trajectory_pose(f, 0, True) for f in (0, 120)])
+    e = synth.expected_pose(gl, 1)
+    assert np.allclose(synth.expected_pose(gl, 0), np.block([[np.eye(3), gl[0][:3, 3:4]], [np.zeros((1, 3)), np.ones((1, 1))]]))
+    # relative motion is preserved: inverse(first) * frame is the same in both frames
+    p0 = synth.expected_pose(gl, 0)
+    assert np.allclose(np.linalg.inv(p0) @ e, np.linalg.inv(gl[0]) @ gl[1])
+    assert not np.allclose(e[:3, 3], gl[1][:3, 3], atol=1e-3)
