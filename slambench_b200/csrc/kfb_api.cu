@@ -652,7 +652,7 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	if (c->integrate_count >= NUPD_SLOTS) CK(cudaMemsetAsync(c->d_nupd + slot, 0, sizeof(unsigned long long), c->stream));
 	p.n_upd = c->d_nupd + slot;
 	// pass 1 cuts every warp-column's visited interval into pieces of `zchunk` slices; pass 2 is persistent
-	// short pieces keep every warp's serial chain short (measured: 256^3 best at 16-32, 512^3 at 64)
+	// short pieces keep every warp's serial chain short (measured: 256^3 best at 16-32, 512^3 at 24-32)
 	{
 		const uint32_t nz = c->z1 - c->z0;
 		uint32_t zc = (nz / 8) & ~7u;   // a multiple of INT_U so a warp can continue into the next piece
@@ -665,8 +665,6 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	p.queue_count = c->d_queue_ctr + 2 * qslot; p.queue_head = p.queue_count + 1;
 	p.queue_next = c->d_queue_ctr + 2 * (qslot ^ 1);
 	{
-		const uint32_t nz = c->z1 - c->z0;
-		(void) nz;
 		const size_t need = (size_t) ((p.sx + 31) / 32) * p.sy;   // one entry per warp-column
 		if (need > c->queue_cap) {
 			if (c->d_queue) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(c->d_queue)); }
