@@ -56,6 +56,13 @@ struct kfb_ctx {
 	kfb_config cfg;
 	int device;
 	cudaStream_t stream;
+	// Second stream: when the LAST thing enqueued on `stream` is a raycast, the next frame's H2D copy, preprocessing and
+	// pyramid do not depend on it (they rewrite buffers whose readers all precede that raycast) and are enqueued here,
+	// behind an event recorded just before the raycast; `stream` then waits for them.  They fill the raycaster's tail
+	// (its persistent warps leave the SMs one by one) instead of starting after it.  Any other enqueue closes the window.
+	cudaStream_t side;
+	cudaEvent_t ev_ray_begin, ev_side_done;
+	bool overlap_enabled, overlap_ok, side_pending;
 	uint32_t cw, ch;
 	int levels;
 	uint32_t lw[KFB_MAX_LEVELS], lh[KFB_MAX_LEVELS];
@@ -168,7 +175,8 @@ static int kfb_fastdiv_ok(float d) {
 }
 
 static inline Mat4 toMat(const float* m) { Mat4 r; memcpy(r.m, m, sizeof r.m); return r; }
-#define LAUNCHED(c) ((c)->st.kernel_launches++)
+// every enqueue on the main stream ends the window in which the next frame's preprocessing may overlap (see kfb_ctx::side)
+#define LAUNCHED(c) ((c)->st.kernel_launches++, (c)->overlap_ok = false, (c)->side_pending = false)
 
 static int launch_init_volume(kfb_ctx* c) {
 	const size_t n = c->slab_voxels, n4 = n / 4;
@@ -248,6 +256,11 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	c->seq = 0; c->integrate_count = 0;
 
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+	CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
+	CK(cudaEventCreateWithFlags(&c->ev_ray_begin, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&c->ev_side_done, cudaEventDisableTiming));
+	{ const char* e = getenv("KFB_NO_OVERLAP"); c->overlap_enabled = !(e && atoi(e) > 0); }
+	c->overlap_ok = false; c->side_pending = false;
 	const size_t P = (size_t) c->cw * c->ch;
 	CK(cudaMalloc(&c->d_vol, c->slab_voxels * sizeof(short2)));
 	CK(cudaMalloc(&c->d_vertex, P * 3 * sizeof(float)));
@@ -369,6 +382,9 @@ int kfb_destroy(kfb_ctx* c) {
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	if (c->d_render) cudaFree(c->d_render);
 	timer_free(c->t_pre); timer_free(c->t_track); timer_free(c->t_int); timer_free(c->t_ray);
+	cudaStreamSynchronize(c->side);
+	cudaEventDestroy(c->ev_ray_begin); cudaEventDestroy(c->ev_side_done);
+	cudaStreamDestroy(c->side);
 	cudaStreamDestroy(c->stream);
 	delete c;
 	return 0;
@@ -398,16 +414,34 @@ static int check_ratio(kfb_ctx* c, uint32_t iw, uint32_t ih, int* ratio) {
 	*ratio = iw / c->cw;
 	return 0;
 }
-static int launch_preprocess(kfb_ctx* c, const uint16_t* d_in, uint32_t iw, int ratio) {
+// the stream the next frame's preprocessing goes to: the side stream (made to wait for everything before the raycast
+// that is still running) inside the overlap window, else the main stream.  Stage timers keep everything serial.
+static cudaStream_t preprocess_stream(kfb_ctx* c, bool* on_side) {
+	*on_side = c->overlap_ok && !(c->timing & 3u);
+	if (*on_side && cudaStreamWaitEvent(c->side, c->ev_ray_begin, 0) != cudaSuccess) { cudaGetLastError(); *on_side = false; }
+	return *on_side ? c->side : c->stream;
+}
+// main stream continues only after the side stream's work; `side_pending`: the pyramid may follow on the side stream
+static int join_side(kfb_ctx* c) {
+	CK(cudaEventRecord(c->ev_side_done, c->side));
+	CK(cudaStreamWaitEvent(c->stream, c->ev_side_done, 0));
+	return 0;
+}
+static int launch_preprocess(kfb_ctx* c, const uint16_t* d_in, uint32_t iw, int ratio, cudaStream_t stream, bool on_side) {
 	Gauss5 g;
 	memcpy(g.g, c->gaussian, sizeof g.g);
 	dim3 grid((c->cw + PP_BX - 1) / PP_BX, (c->ch + PP_BY - 1) / PP_BY), block(PP_BX, PP_BY);
 	const int slot = (int) (c->preprocess_count++ & 1);
-	k_mm2m_bilateral<<<grid, block, 0, c->stream>>>(d_in, iw, ratio, c->d_floatDepth, c->d_scaled[0], c->cw, c->ch, g, c_e_delta,
+	k_mm2m_bilateral<<<grid, block, 0, stream>>>(d_in, iw, ratio, c->d_floatDepth, c->d_scaled[0], c->cw, c->ch, g, c_e_delta,
 			c->d_dmax + slot, c->d_dmax + (slot ^ 1));
 	c->dmax_slot = slot;
 	LAUNCHED(c);
 	CK(cudaGetLastError());
+	if (on_side) {
+		int rc = join_side(c);
+		if (rc) return rc;
+		c->side_pending = true;
+	}
 	return 0;
 }
 static int ensure_input(kfb_ctx* c, size_t bytes) {
@@ -441,8 +475,11 @@ int kfb_preprocess(kfb_ctx* c, const uint16_t* depth, uint32_t iw, uint32_t ih) 
 			pinned = true;
 		} else cudaGetLastError();
 	}
+	bool on_side = false;
+	cudaStream_t ps = c->stream;
 	if (pinned) {
-		CK(cudaMemcpyAsync(c->d_input, depth, bytes, cudaMemcpyHostToDevice, c->stream));
+		ps = preprocess_stream(c, &on_side);
+		CK(cudaMemcpyAsync(c->d_input, depth, bytes, cudaMemcpyHostToDevice, ps));
 	} else {
 		if (c->stage_bytes < bytes) {
 			if (c->h_stage) CK(cudaFreeHost(c->h_stage));
@@ -454,7 +491,7 @@ int kfb_preprocess(kfb_ctx* c, const uint16_t* depth, uint32_t iw, uint32_t ih) 
 		CK(cudaMemcpyAsync(c->d_input, c->h_stage, bytes, cudaMemcpyHostToDevice, c->stream));
 	}
 	c->st.h2d_bytes += bytes;
-	rc = launch_preprocess(c, c->d_input, iw, ratio);
+	rc = launch_preprocess(c, c->d_input, iw, ratio, ps, on_side);
 	timer_end(c, c->t_pre, 1u);
 	return rc;
 }
@@ -465,7 +502,9 @@ int kfb_preprocess_device(kfb_ctx* c, const uint16_t* d_depth, uint32_t iw, uint
 	int ratio, rc;
 	if ((rc = check_ratio(c, iw, ih, &ratio))) return rc;
 	timer_begin(c, c->t_pre, 1u);
-	rc = launch_preprocess(c, d_depth, iw, ratio);
+	bool on_side = false;
+	cudaStream_t ps = preprocess_stream(c, &on_side);
+	rc = launch_preprocess(c, d_depth, iw, ratio, ps, on_side);
 	timer_end(c, c->t_pre, 1u);
 	return rc;
 }
@@ -489,9 +528,12 @@ static int launch_pyramid(kfb_ctx* c, const float k[4]) {
 		hm_inverse_camera_matrix(p.invK[l].m, ks);
 	}
 	p.first[c->levels] = first;
-	k_pyramid<<<(first + 255) / 256, 256, 0, c->stream>>>(p);
+	// right behind a preprocessing that went to the side stream: follow it there (same window, same readers)
+	const bool on_side = c->side_pending && !(c->timing & 3u);
+	k_pyramid<<<(first + 255) / 256, 256, 0, on_side ? c->side : c->stream>>>(p);
 	LAUNCHED(c);
 	CK(cudaGetLastError());
+	if (on_side) return join_side(c);
 	return 0;
 }
 
@@ -725,9 +767,11 @@ static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP
 	p.nearPlane = nearP; p.farPlane = farP; p.step = step; p.largestep = largestep;
 	const int slot = (int) (c->ray_launches++ & 1);
 	p.tile_next = c->d_tile_ctr + slot; p.tile_reset = c->d_tile_ctr + (slot ^ 1);
+	if (c->overlap_enabled) CK(cudaEventRecord(c->ev_ray_begin, c->stream));
 	k_raycast<<<c->ray_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p);
 	LAUNCHED(c);
 	CK(cudaGetLastError());
+	c->overlap_ok = c->overlap_enabled;   // until anything else is enqueued
 	return 0;
 }
 
