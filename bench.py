@@ -337,6 +337,8 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
                 "preprocess": d["ms_preprocess"] / K_steps, "track": d["ms_track"] / K_steps,
                 "integrate": d["ms_integrate"] / max(1, d["frames_integrated"]), "raycast": d["ms_raycast"] / K_steps,
                 "icp_iterations": d["icp_iterations_total"] / K_steps, "launches": d["kernel_launches"] / K_steps,
+                "note": "separate pass with per-stage CUDA events, which keeps the stages serial; in the timed region frame k+1's "
+                        "copy + preprocess + pyramid overlap frame k's raycast, so the stages sum to more than ms_per_step",
             }
         if world == 1 and not args.no_cpu_baseline:
             done, secs, kind, cores, name = run_cpu_frames(depth_np, args.volume, min(4, args.warmup), args.steps, args.cpu_budget)
