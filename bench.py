@@ -236,6 +236,10 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
             def frame(f):
+                if not resident and args.compute_frame:
+                    # the reference's one-call entry point (Kfusion::computeFrame, kernels.h:158-166): same four stages
+                    g.computeFrame(depth_np[f], None, K, 1, 1, ICP_THRESHOLD, MU, f)
+                    return g.getTracked(), g.getIntegrated(), g.getPose()
                 if resident:
                     g.preprocessing_device(dev[f].data_ptr(), (W_IMG, H_IMG))
                 else:
@@ -480,6 +484,8 @@ def main():
     ap.add_argument("--volume", type=int, default=512, help="volume resolution N (N^3 voxels); default = BASELINE configs[1]")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compute-frame", action="store_true",
+                    help="e2e arm: one Kfusion::computeFrame call per frame instead of the four stage calls of benchmark.cpp")
     ap.add_argument("--no-breakdown", action="store_true", help="skip the extra per-stage timing pass")
     ap.add_argument("--mode", default="sequences", choices=["sequences", "sharded"],
                     help="N > 1: one independent sequence per GPU (weak scaling, default) or ONE sequence on a z-slab sharded volume (strong)")
