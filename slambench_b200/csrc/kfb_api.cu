@@ -56,12 +56,13 @@ struct kfb_ctx {
 	kfb_config cfg;
 	int device;
 	cudaStream_t stream;
-	// Second stream: when the LAST thing enqueued on `stream` is a raycast, the next frame's H2D copy, preprocessing and
-	// pyramid do not depend on it (they rewrite buffers whose readers all precede that raycast) and are enqueued here,
-	// behind an event recorded just before the raycast; `stream` then waits for them.  They fill the raycaster's tail
-	// (its persistent warps leave the SMs one by one) instead of starting after it.  Any other enqueue closes the window.
+	// Second stream: when the LAST things enqueued on `stream` are an integrate and / or a raycast, the next frame's H2D
+	// copy, preprocessing and pyramid do not depend on them (they rewrite buffers whose readers all precede that integrate;
+	// the raw depth and its maximum, which integrate reads, are double- / triple-buffered) and are enqueued here, behind an
+	// event recorded just before the integrate; `stream` then waits for them.  They fill the tails of the two persistent
+	// kernels (whose warps leave the SMs one by one) instead of starting after them.  Any other enqueue closes the window.
 	cudaStream_t side;
-	cudaEvent_t ev_ray_begin, ev_side_done;
+	cudaEvent_t ev_window, ev_side_done;
 	bool overlap_enabled, overlap_ok, side_pending;
 	uint32_t cw, ch;
 	int levels;
@@ -76,7 +77,8 @@ struct kfb_ctx {
 	uint32_t z0, z1;            // slab
 	size_t slab_voxels;
 	float *d_vertex, *d_normal; // raycast maps
-	float* d_floatDepth;
+	float* d_floatDepth;        // the CURRENT raw depth (= d_fd[fd_cur]); preprocessing writes the other buffer and flips
+	float* d_fd[2]; int fd_cur;
 	float* d_scaled[KFB_MAX_LEVELS];
 	float* d_inV[KFB_MAX_LEVELS];
 	float* d_inN[KFB_MAX_LEVELS];
@@ -94,7 +96,7 @@ struct kfb_ctx {
 	float* h_out32_dev;
 	uint32_t seq;
 	unsigned long long* d_nupd; // NUPD_SLOTS per-integrate counters
-	unsigned int* d_dmax;       // two slots: bit pattern of max(floatDepth), written by preprocess (ping-pong)
+	unsigned int* d_dmax;       // three rotating slots: bit pattern of max(floatDepth), written by preprocess
 	uint32_t int_zchunk;        // integrate piece length override (KFB_INT_ZCHUNK, tuning)
 	uint2* d_queue; size_t queue_cap;   // integrate work list
 	BrickMap brick;             // brick flags for the raycaster (whole-volume contexts only)
@@ -257,7 +259,7 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
-	CK(cudaEventCreateWithFlags(&c->ev_ray_begin, cudaEventDisableTiming));
+	CK(cudaEventCreateWithFlags(&c->ev_window, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&c->ev_side_done, cudaEventDisableTiming));
 	{ const char* e = getenv("KFB_NO_OVERLAP"); c->overlap_enabled = !(e && atoi(e) > 0); }
 	c->overlap_ok = false; c->side_pending = false;
@@ -265,7 +267,10 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	CK(cudaMalloc(&c->d_vol, c->slab_voxels * sizeof(short2)));
 	CK(cudaMalloc(&c->d_vertex, P * 3 * sizeof(float)));
 	CK(cudaMalloc(&c->d_normal, P * 3 * sizeof(float)));
-	CK(cudaMalloc(&c->d_floatDepth, P * sizeof(float)));
+	CK(cudaMalloc(&c->d_fd[0], P * sizeof(float)));
+	CK(cudaMalloc(&c->d_fd[1], P * sizeof(float)));
+	CK(cudaMemsetAsync(c->d_fd[1], 0, P * sizeof(float), c->stream));
+	c->fd_cur = 0; c->d_floatDepth = c->d_fd[0];
 	// calloc'd in the reference (cpp/kernels.cpp:75-98): first-frame reads of `vertex`/`normal` see zeros
 	CK(cudaMemsetAsync(c->d_vertex, 0, P * 3 * sizeof(float), c->stream));
 	CK(cudaMemsetAsync(c->d_normal, 0, P * 3 * sizeof(float), c->stream));
@@ -306,8 +311,8 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	}
 	CK(cudaHostGetDevicePointer(&c->h_out32_dev, c->h_out32, 0));
 	CK(cudaMalloc(&c->d_nupd, NUPD_SLOTS * sizeof(unsigned long long)));
-	CK(cudaMalloc(&c->d_dmax, 2 * sizeof(unsigned int)));
-	CK(cudaMemsetAsync(c->d_dmax, 0, 2 * sizeof(unsigned int), c->stream));
+	CK(cudaMalloc(&c->d_dmax, 3 * sizeof(unsigned int)));
+	CK(cudaMemsetAsync(c->d_dmax, 0, 3 * sizeof(unsigned int), c->stream));
 	c->dmax_slot = -1; c->preprocess_count = 0;
 	{ const char* e = getenv("KFB_INT_ZCHUNK"); c->int_zchunk = e ? (uint32_t) atoi(e) : 0; }
 	c->d_queue = nullptr; c->queue_cap = 0; c->int_launches = 0;
@@ -367,7 +372,7 @@ int kfb_destroy(kfb_ctx* c) {
 	for (int i = 0; i < c->n_reg; ++i) cudaHostUnregister((void*) c->reg_ptr[i]);
 	for (int i = 0; i < KFB_MAX_SLABS; ++i) if (c->peer_ptrs[i]) cudaIpcCloseMemHandle(c->peer_ptrs[i]);
 	if (c->brick.flag) cudaFree(c->brick.flag);
-	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_floatDepth);
+	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_fd[0]); cudaFree(c->d_fd[1]);
 	for (int l = 0; l < c->levels; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
 	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax); cudaFree(c->d_queue_ctr); cudaFree(c->d_tile_ctr); if (c->d_tile_cost) cudaFree(c->d_tile_cost); if (c->d_queue) cudaFree(c->d_queue);
 	if (c->d_icp_prof) {
@@ -383,7 +388,7 @@ int kfb_destroy(kfb_ctx* c) {
 	if (c->d_render) cudaFree(c->d_render);
 	timer_free(c->t_pre); timer_free(c->t_track); timer_free(c->t_int); timer_free(c->t_ray);
 	cudaStreamSynchronize(c->side);
-	cudaEventDestroy(c->ev_ray_begin); cudaEventDestroy(c->ev_side_done);
+	cudaEventDestroy(c->ev_window); cudaEventDestroy(c->ev_side_done);
 	cudaStreamDestroy(c->side);
 	cudaStreamDestroy(c->stream);
 	delete c;
@@ -418,7 +423,7 @@ static int check_ratio(kfb_ctx* c, uint32_t iw, uint32_t ih, int* ratio) {
 // that is still running) inside the overlap window, else the main stream.  Stage timers keep everything serial.
 static cudaStream_t preprocess_stream(kfb_ctx* c, bool* on_side) {
 	*on_side = c->overlap_ok && !(c->timing & 3u);
-	if (*on_side && cudaStreamWaitEvent(c->side, c->ev_ray_begin, 0) != cudaSuccess) { cudaGetLastError(); *on_side = false; }
+	if (*on_side && cudaStreamWaitEvent(c->side, c->ev_window, 0) != cudaSuccess) { cudaGetLastError(); *on_side = false; }
 	return *on_side ? c->side : c->stream;
 }
 // main stream continues only after the side stream's work; `side_pending`: the pyramid may follow on the side stream
@@ -431,9 +436,13 @@ static int launch_preprocess(kfb_ctx* c, const uint16_t* d_in, uint32_t iw, int 
 	Gauss5 g;
 	memcpy(g.g, c->gaussian, sizeof g.g);
 	dim3 grid((c->cw + PP_BX - 1) / PP_BX, (c->ch + PP_BY - 1) / PP_BY), block(PP_BX, PP_BY);
-	const int slot = (int) (c->preprocess_count++ & 1);
-	k_mm2m_bilateral<<<grid, block, 0, stream>>>(d_in, iw, ratio, c->d_floatDepth, c->d_scaled[0], c->cw, c->ch, g, c_e_delta,
-			c->d_dmax + slot, c->d_dmax + (slot ^ 1));
+	// the raw depth and its maximum go to buffers the integrate that may still be running does not read: the other
+	// floatDepth buffer, and slot n % 3 of max(depth) (slot (n + 1) % 3 is zeroed for the next frame)
+	const int slot = (int) (c->preprocess_count++ % 3);
+	const int nb = c->fd_cur ^ 1;
+	k_mm2m_bilateral<<<grid, block, 0, stream>>>(d_in, iw, ratio, c->d_fd[nb], c->d_scaled[0], c->cw, c->ch, g, c_e_delta,
+			c->d_dmax + slot, c->d_dmax + (slot + 1) % 3);
+	c->fd_cur = nb; c->d_floatDepth = c->d_fd[nb];
 	c->dmax_slot = slot;
 	LAUNCHED(c);
 	CK(cudaGetLastError());
@@ -674,6 +683,9 @@ int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracki
 
 // --------------------------------------------------------------------------- integration
 static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, float mu, float maxweight) {
+	// everything the next frame's preprocessing rewrites has been read by now, except the raw depth and its maximum,
+	// which are double- / triple-buffered: its window (kfb_ctx::side) opens here
+	if (c->overlap_enabled) CK(cudaEventRecord(c->ev_window, c->stream));
 	IntegrateParams p;
 	p.vol = c->d_vol;
 	p.sx = c->cfg.volume_res[0]; p.sy = c->cfg.volume_res[1]; p.sz = c->cfg.volume_res[2];
@@ -725,6 +737,7 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	CK(cudaGetLastError());
 	c->integrate_count++;
 	c->st.frames_integrated++;
+	c->overlap_ok = c->overlap_enabled;   // until anything but the raycast is enqueued
 	return 0;
 }
 
@@ -767,7 +780,8 @@ static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP
 	p.nearPlane = nearP; p.farPlane = farP; p.step = step; p.largestep = largestep;
 	const int slot = (int) (c->ray_launches++ & 1);
 	p.tile_next = c->d_tile_ctr + slot; p.tile_reset = c->d_tile_ctr + (slot ^ 1);
-	if (c->overlap_enabled) CK(cudaEventRecord(c->ev_ray_begin, c->stream));
+	// window for the next frame's preprocessing: already open when this raycast directly follows an integrate
+	if (c->overlap_enabled && !c->overlap_ok) CK(cudaEventRecord(c->ev_window, c->stream));
 	k_raycast<<<c->ray_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p);
 	LAUNCHED(c);
 	CK(cudaGetLastError());
