@@ -1028,6 +1028,9 @@ int kfb_slab_import(kfb_ctx* c, int rank, int world, const uint8_t* handles64, c
 	CK(cudaSetDevice(c->device));
 	c->rank = rank; c->world = world;
 	c->view_all.n_slabs = world;
+	// z-slab mode interleaves collectives of the caller on this stream; its numbers were measured without the side-stream
+	// overlap, and the overlap has not been validated on several GPUs: keep those contexts strictly serial
+	if (world > 1) { c->overlap_enabled = false; c->overlap_ok = false; c->side_pending = false; }
 	// each rank flags only what ITS slices touch: without the caller's merge the raycaster must not skip
 	if (!(c->cfg.flags & KFB_FLAG_BRICKS_MERGED)) c->view_all.brick = nullptr;
 	for (int r = 0; r < world; ++r) {
