@@ -138,22 +138,42 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- CPU baseline
-def run_cpu_frames(depth, vres: int, n_warm: int, n_timed: int, budget_s: float | None):
+def set_omp_threads(n: int) -> int:
+    """Make the OpenMP runtime of the CPU legs use `n` threads and return what it will really use.  torchrun
+    pre-sets OMP_NUM_THREADS=1 in every rank, so the variable is overwritten (not defaulted) and, because a
+    runtime that is already loaded no longer reads it, omp_set_num_threads is called on libgomp as well."""
+    import ctypes  # noqa: PLC0415
+
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    try:
+        gomp = ctypes.CDLL("libgomp.so.1")
+        gomp.omp_set_num_threads(ctypes.c_int(n))
+        return int(gomp.omp_get_max_threads())
+    except OSError:
+        return n
+
+
+def run_cpu_frames(depth, vres: int, n_warm: int, n_timed: int, budget_s: float | None, single_thread: bool = False):
     """Drive the reference CPU backend over depth[0 : n_warm + n_timed]; returns
     (frames timed, seconds, kind, cores, impl name).  Test-infrastructure code path: this is the one
-    place bench.py executes oracle/ as the thing measured (cpu_baseline / --impl reference)."""
+    place bench.py executes oracle/ as the thing measured (cpu_baseline / --impl reference).
+    `single_thread`: the reference's `-cpp` build (kfusion-benchmark-cpp's backend) instead of `-openmp`."""
     from oracle import cpu_backend as cb
     from slambench_b200 import synth
 
-    if os.path.exists(cb.REF_OMP_LIB):
-        lib, kind, cores = cb.REF_OMP_LIB, "reference", host_cores()
+    if single_thread and os.path.exists(cb.REF_LIB):
+        lib, kind, cores = cb.REF_LIB, "reference", 1
+    elif os.path.exists(cb.REF_OMP_LIB):
+        lib, kind, cores = cb.REF_OMP_LIB, "reference", 1 if single_thread else host_cores()
     elif os.path.exists(cb.REF_LIB):
         lib, kind, cores = cb.REF_LIB, "reference", 1
     else:
         cb.build_port()
-        lib, kind, cores = cb.PORT_LIB, "port", host_cores()   # the C restatement is built with -fopenmp too
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+        lib, kind, cores = cb.PORT_LIB, "port", 1 if single_thread else host_cores()   # the C restatement is built with -fopenmp too
     be = cb.CpuKfusion(lib)
+    used = set_omp_threads(cores)
+    if lib != cb.REF_LIB:
+        cores = used                                   # the thread count the OpenMP runtime reports, not the wish
     K = np.array(synth.K_DEFAULT, np.float32)
     T0 = (np.array(synth.INIT_POS_FACTOR, np.float32) * np.float32(VOLUME_DIM)).astype(np.float32)
     be.create((W_IMG, H_IMG), vres, VOLUME_DIM, T0, PYRAMID)
@@ -229,8 +249,10 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
     dev = host.to(f"cuda:{local_rank}", non_blocking=False)          # HBM-resident frames (value arm)
     frame_bytes = W_IMG * H_IMG * 2
 
-    def run(resident: bool, time_mask: int):
-        """W warm-up frames, then exactly K timed frames.  Returns dict of measurements."""
+    def run(resident: bool, time_mask: int, collective: bool = True):
+        """W warm-up frames, then exactly K timed frames.  Returns dict of measurements.  `collective=False`: a pass
+        that only some ranks execute (the per-stage breakdown on rank 0) must not enter the cross-rank barrier."""
+        sync = barrier if collective else torch.cuda.synchronize
         with kf.Kfusion((W_IMG, H_IMG), args.volume, VOLUME_DIM, T0, PYRAMID, device=local_rank) as g:
             stream = torch.cuda.ExternalStream(g.stream(), device=local_rank)
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -255,7 +277,7 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
             g.synchroniseDevices()
             g.enable_timing(time_mask)
             g.reset_stats()
-            barrier()
+            sync()
             clocks = ClockSampler(local_rank)
             if time_mask and rank == 0:
                 clocks.start()
@@ -270,7 +292,7 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
             torch.cuda.synchronize()
             wall = time.perf_counter() - t0
             ck = clocks.stop() if (time_mask and rank == 0) else None
-            barrier()
+            sync()
             ms = ev0.elapsed_time(ev1)
             st = g.stats()
             err = float(np.abs(pose[:3, 3] - synth.expected_pose(gt, n - 1)[:3, 3]).max())
@@ -280,7 +302,8 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
     depth_np = host.numpy()
     res = run(resident=True, time_mask=4)        # value: HBM-resident input; integrate timed with CUDA events
     e2e = run(resident=False, time_mask=0)       # e2e: pinned host frames, H2D + D2H inside the timed region
-    diag = run(resident=True, time_mask=15) if rank == 0 and not args.no_breakdown else None
+    # rank 0 only, and therefore without any collective inside (round 1 deadlocked here at N > 1)
+    diag = run(resident=True, time_mask=15, collective=False) if rank == 0 and not args.no_breakdown else None
 
     def reduce_max(x: float) -> float:
         if dist is None:
@@ -349,6 +372,28 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
             line["cpu_baseline"] = {"value": done / secs, "unit": UNIT, "cores": cores, "kind": kind, "backend": name,
                                     "sample": f"{done} frames (from frame {min(4, args.warmup)}) of the same sequence and volume, "
                                               f"whole pipeline per frame, bounded to ~{args.cpu_budget:.0f} s"}
+            # north_star: next to kfusion-benchmark-openmp AND -cpp: the reference's single-thread backend, same frames
+            d1, s1, kind1, _, name1 = run_cpu_frames(depth_np, args.volume, min(4, args.warmup), min(args.steps, 8),
+                                                     args.cpu_budget / 2, single_thread=True)
+            line["cpu_baseline"]["cpp_1thread"] = {"value": d1 / s1, "unit": UNIT, "cores": 1, "kind": kind1, "backend": name1,
+                                                   "sample": f"{d1} frames (from frame {min(4, args.warmup)}), bounded to ~{args.cpu_budget / 2:.0f} s"}
+    sh = None
+    if dist is not None and not args.no_sharded:
+        # N > 1: the driver only ever runs `bench.py --gpus N`, so the z-slab mode (BASELINE configs[3]: ONE sequence,
+        # 1024^3 cut into N slabs; configs[4]: 2048^3, at 8 GPUs) is timed in the same run and reported next to `value`
+        sh = {}
+        vols = [1024] + ([2048] if world >= 8 else [])
+        for vol in vols:
+            r = sharded_run(args, rank, world, local_rank, torch, dist, vol, args.sharded_steps, max(4, min(args.warmup, 8)))
+            if rank == 0:
+                sh[str(vol)] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "scaling": "strong",
+                                "steps": r["steps"], "workload": r["config"]["workload"], "parallelism": r["config"]["parallelism"],
+                                "slabs": r["config"]["slabs"], "tracked_frames": r["config"]["tracked_frames"],
+                                "final_pose_err_m": r["config"]["final_pose_err_m"], "roofline": r["roofline"],
+                                "stage_ms_per_frame": r["stage_ms_per_frame"]}
+    if rank == 0:
+        if sh:
+            line["sharded"] = sh
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -374,18 +419,26 @@ def render_sequence_distributed(total: int, rank: int, world: int, torch, dist, 
 
 
 def sharded_arm(args, rank: int, world: int, local_rank: int):
-    """ONE sequence, the volume cut into z-slabs over the ranks (BASELINE configs[3], [4]): integrate local, raycast
-    over NVLink peer slabs + NCCL all-gather, ICP replicated or all-reduced.  Strong scaling: the work is fixed."""
+    """`--mode sharded`: the z-slab run alone, printed as the bench line (strong scaling: the work is fixed)."""
     import torch
     import torch.distributed as dist
 
-    from slambench_b200 import sharded, synth
-
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = sharded_run(args, rank, world, local_rank, torch, dist, args.volume, args.steps, args.warmup)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
+
+
+def sharded_run(args, rank: int, world: int, local_rank: int, torch, dist, volume: int, steps: int, warmup: int):
+    """ONE sequence, the volume cut into z-slabs over the ranks (BASELINE configs[3], [4]): integrate local, raycast
+    over NVLink peer slabs, ICP replicated or all-reduced.  Returns the bench line (rank 0) or None."""
+    from slambench_b200 import sharded, synth
+
     K = np.array(synth.K_DEFAULT, np.float32)
     T0 = (np.array(synth.INIT_POS_FACTOR, np.float32) * np.float32(VOLUME_DIM)).astype(np.float32)
-    n = args.warmup + args.steps
+    n = warmup + steps
     n_diag = 6                                    # extra frames for the per-stage breakdown (after the timed region)
     if n + n_diag <= 200:
         depth_np, gt = synth.make_sequence(n + n_diag, long_run=False)
@@ -395,7 +448,7 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
         depth_np, gt = render_sequence_distributed(n + n_diag, rank, world, torch, dist, f"cuda:{local_rank}")
     host = torch.from_numpy(depth_np).pin_memory()
     depth_np = host.numpy()
-    with sharded.ShardedKfusion((W_IMG, H_IMG), args.volume, VOLUME_DIM, T0, PYRAMID, rank=rank, world=world, device=local_rank,
+    with sharded.ShardedKfusion((W_IMG, H_IMG), volume, VOLUME_DIM, T0, PYRAMID, rank=rank, world=world, device=local_rank,
                                 icp_mode=args.icp_mode, balance_k=None if args.even_slabs else K,
                                 balance_far=float(depth_np[0].max()) / 1000.0) as s:
         g = s.local
@@ -409,7 +462,7 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
             s.raycasting(K, MU, f)
             return tr
 
-        for f in range(args.warmup):
+        for f in range(warmup):
             frame(f)
         s.synchroniseDevices()
         g.enable_timing(4)
@@ -419,7 +472,7 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
         t0 = time.perf_counter()
         ev0.record(stream)
         tracked = 0
-        for f in range(args.warmup, n):
+        for f in range(warmup, n):
             tracked += frame(f)
         ev1.record(stream)
         s.synchroniseDevices()
@@ -454,15 +507,15 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
             alg = (8.0 * float(tsum[1]) + 4.0 * P_PIX * n_int * world) / n_int          # all slabs together
             t_int = float(tmax[2]) / n_int * 1e-3                                          # slowest slab
             line = {
-                "metric": METRIC, "value": args.steps / (ms_all * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": ms_all / args.steps, "higher_is_better": True, "scaling": "strong",
+                "metric": METRIC, "value": steps / (ms_all * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps,
+                "warmup": warmup, "ms_per_step": ms_all / steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": workload_name(args.volume), "volume": args.volume, "frames": n,
+                "config": {"workload": workload_name(volume), "volume": volume, "frames": n,
                            "parallelism": f"z-slab x{world}: integrate local, raycast via NVLink peer slabs + NCCL all-gather, ICP {args.icp_mode}",
                            "slabs": [list(z) for z in s.slabs],
                            "tracked_frames": int(tracked), "final_pose_err_m": err},
-                "e2e": {"value": args.steps / (ms_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W_IMG * H_IMG * 2,
-                        "d2h_bytes_per_step": st["d2h_bytes"] / args.steps},
+                "e2e": {"value": steps / (ms_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W_IMG * H_IMG * 2,
+                        "d2h_bytes_per_step": st["d2h_bytes"] / steps},
                 "gpu_launches": int(st["kernel_launches"]) * world,
                 "roofline": {"bound": "hbm", "kernel": "k_integrate_run", "achieved": alg / t_int / 1e9, "peak": peak * world, "unit": "GB/s",
                              "frac": alg / t_int / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src + f" x{world}",
@@ -471,8 +524,8 @@ def sharded_arm(args, rank: int, world: int, local_rank: int):
                                        "integrate+flag merge": float(tstage[2]), "raycast+all-gather": float(tstage[3]),
                                        "note": "synchronised after every stage, max over ranks"},
             }
-            print(json.dumps(line), flush=True)
-    dist.destroy_process_group()
+            return line
+    return None
 
 
 def main():
@@ -490,6 +543,8 @@ def main():
     ap.add_argument("--mode", default="sequences", choices=["sequences", "sharded"],
                     help="N > 1: one independent sequence per GPU (weak scaling, default) or ONE sequence on a z-slab sharded volume (strong)")
     ap.add_argument("--icp-mode", default="replicated", choices=["replicated", "allreduce"])
+    ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the extra z-slab (configs[3]/[4]) runs")
+    ap.add_argument("--sharded-steps", type=int, default=20, help="timed frames of the z-slab runs added to the N > 1 line")
     ap.add_argument("--even-slabs", action="store_true", help="sharded mode: equal z-slabs instead of the load-aware boundaries")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes/launch of k_integrate from the ncu capture in profiles/")
     args = ap.parse_args()

@@ -33,7 +33,7 @@ typedef struct kfb_ctx kfb_ctx;
 #define KFB_FLAG_ICP_HOST_SOLVE 0x1u   /* one k_track_reduce launch + host 6x6 solve per ICP iteration: the reference's control flow
                                          verbatim (A/B check); default = one persistent cooperative kernel per frame            */
 #define KFB_FLAG_TRACK_STATUS   0x2u   /* keep the per-pixel ICP status plane that renderTrack visualises           */
-#define KFB_FLAG_RESERVED_4     0x4u   /* reserved (was: CUDA-graph switch); ignored                                   */
+#define KFB_FLAG_INTEGRATE_V1   0x4u   /* integrate with round 1's per-voxel-decision kernels instead of the brick-classified ones (A/B) */
 #define KFB_FLAG_INTEGRATE_NO_CULL 0x8u /* integrate visits every voxel with the reference's full expression (A/B check) */
 #define KFB_FLAG_RAYCAST_NO_SKIP 0x10u  /* raycast evaluates every sample (no brick flags) (A/B check)                    */
 #define KFB_FLAG_BRICKS_MERGED 0x20u    /* z-slab mode: the caller merges (element-wise max over ranks) KFB_BUF_BRICKFLAGS between
@@ -80,6 +80,7 @@ enum kfb_buffer {
 	KFB_BUF_INPUTDEPTH = 12,  /* uint16[in_w*in_h] device copy of the last sensor frame                      */
 	KFB_BUF_REDUCTION_DEV = 13, /* float[32] DEVICE copy of the last track+reduce result (multi-GPU all-reduce operand) */
 	KFB_BUF_BRICKFLAGS = 14,  /* uint8[ceil(N/8)^3] brick flags of the WHOLE volume (see KFB_FLAG_BRICKS_MERGED)            */
+	KFB_BUF_BRICKCLASS = 16,  /* uint8[ceil(slab/8)][ceil(N/8)][ceil(N/8)] classes of the LAST integrate's bricks: 0 skip, 1 free (sdf == 1), 2 per-voxel */
 	KFB_BUF_RAYTILECOST = 15  /* uint32[ceil(h/4)][ceil(w/8)] SM cycles per raycast tile, last launch (env KFB_RAY_TILECOST=1)   */
 };
 

@@ -58,6 +58,15 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """A tuning variant of the same library (extra -D macros) next to the product: libkfb200_<name>.so.  Selected at run
+    time with KFB_LIB=<path> (kfusion.load_library); never loaded by default."""
+    out = os.path.join(PKG, f"libkfb200_{name}.so")
+    cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-shared", "-o", out, os.path.join(CSRC, "kfb_api.cu"), "-ldl"]
+    subprocess.check_call(cmd, cwd=CSRC)
+    return out
+
+
 def build_benchmark(force: bool = False) -> str | None:
     """`kfusion-benchmark-b200`: the reference's UNMODIFIED benchmark.cpp + PowerMonitor.cpp linked
     against our Kfusion backend glue (csrc/kfusion_b200.cpp) and libkfb200.so.  Needs the reference

@@ -5,6 +5,7 @@
 // CUDA device and fails with an error code otherwise.
 #include "../../include/kfb200.h"
 #include "kfb_kernels.cuh"
+#include "kfb_integrate2.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -99,10 +100,17 @@ struct kfb_ctx {
 	unsigned int* d_dmax;       // three rotating slots: bit pattern of max(floatDepth), written by preprocess
 	uint32_t int_zchunk;        // integrate piece length override (KFB_INT_ZCHUNK, tuning)
 	uint2* d_queue; size_t queue_cap;   // integrate work list
+	// integrate v2: (min, max) depth pyramids (one per raw-depth buffer), brick classes of the current launch
+	float2* d_mip[2]; DepthMip mip[2]; bool mip_valid[2];
+	unsigned int* d_mip_ticket;
+	unsigned char* d_cls; size_t cls_bytes;
+	uint2 *d_qmixed, *d_qfree;           // integrate v2 work items (worst-case sized at create)
+	unsigned int* d_q2ctr;               // 2 slots x {#mixed, #free, next}
+	unsigned long long* d_ckpt; unsigned int ckpt_cap;   // running-value checkpoints of the MIXED items (768 B each)
 	BrickMap brick;             // brick flags for the raycaster (whole-volume contexts only)
 	bool brick_off;
 	unsigned int* d_queue_ctr;  // 2 slots x {count, head}
-	int int_grid;               // persistent CTAs of k_integrate_run
+	int int_grid, int_grid2;    // persistent CTAs of k_integrate_run / k_integrate_run2
 	int ray_grid;               // persistent CTAs of k_raycast
 	unsigned int* d_tile_ctr;   // two alternating tile counters
 	unsigned int* d_tile_cost;  // KFB_RAY_TILECOST=1: cycles per raycast tile of the last launch (diagnostics)
@@ -209,20 +217,9 @@ int kfb_k_check_pose(float pose[16], const float old_pose[16], const float red[3
 	return 0;
 }
 
-int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
-	if (!cfg || !out) return set_err(KFB_E_ARG, "null argument");
-	if (cfg->n_levels < 1 || cfg->n_levels > 3)
-		return set_err(KFB_E_ARG, "pyramid levels must be 1..3 (got %d)", cfg->n_levels);
-	if (cfg->compute_w == 0 || cfg->compute_h == 0 || cfg->volume_res[0] == 0 || cfg->volume_res[1] == 0 || cfg->volume_res[2] == 0)
-		return set_err(KFB_E_ARG, "empty image or volume");
-	if ((cfg->compute_w >> (cfg->n_levels - 1)) == 0 || (cfg->compute_h >> (cfg->n_levels - 1)) == 0)
-		return set_err(KFB_E_ARG, "image too small for %d pyramid levels", cfg->n_levels);
-	int ndev = 0;
-	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-		return set_err(KFB_E_CUDA, "no CUDA device: libkfb200 has no CPU fallback");
-	if (cfg->device < 0 || cfg->device >= ndev) return set_err(KFB_E_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+// everything kfb_create allocates; on any failure the caller (kfb_create) destroys the partially built context
+static int create_impl(const kfb_config* cfg, kfb_ctx* c) {
 	CK(cudaSetDevice(cfg->device));
-	kfb_ctx* c = new kfb_ctx();
 	memset(&c->st, 0, sizeof c->st);
 	c->cfg = *cfg;
 	{ const char* e = getenv("KFB_FLAGS"); if (e) c->cfg.flags |= (uint32_t) strtoul(e, nullptr, 0); }   // experiments: OR extra flags in
@@ -248,14 +245,12 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	}
 	c->z0 = cfg->slab_z0; c->z1 = cfg->slab_z1;
 	if (c->z0 == 0 && c->z1 == 0) c->z1 = cfg->volume_res[2];
-	if (c->z1 > cfg->volume_res[2] || c->z0 >= c->z1) { delete c; return set_err(KFB_E_ARG, "bad z-slab [%u,%u)", cfg->slab_z0, cfg->slab_z1); }
+	if (c->z1 > cfg->volume_res[2] || c->z0 >= c->z1) return set_err(KFB_E_ARG, "bad z-slab [%u,%u)", cfg->slab_z0, cfg->slab_z1);
+	// integrate decides per 8^3 brick and the raycaster's brick flags are per 8 slices: a slab starts on a brick layer
+	if (c->z0 % 8 != 0) return set_err(KFB_E_ARG, "z-slab start %u is not a multiple of 8 (brick layers)", c->z0);
 	c->slab_voxels = (size_t) cfg->volume_res[0] * cfg->volume_res[1] * (c->z1 - c->z0);
 	c->timing = 0;
 	c->rank = 0; c->world = 1; c->band0 = 0; c->band1 = cfg->compute_h;
-	c->n_reg = 0;
-	c->d_input = nullptr; c->input_bytes = 0; c->h_stage = nullptr; c->stage_bytes = 0;
-	c->d_render = nullptr; c->render_bytes = 0;
-	c->seq = 0; c->integrate_count = 0;
 
 	CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
 	CK(cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking));
@@ -296,7 +291,6 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	CK(cudaMalloc(&c->d_bar, 4 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_bar, 0, 4 * sizeof(unsigned int), c->stream));
 	CK(cudaMalloc(&c->d_pose, 16 * sizeof(float)));
-	c->d_icp_prof = nullptr;
 	if (getenv("KFB_ICP_PROFILE")) { CK(cudaMalloc(&c->d_icp_prof, 8 * sizeof(unsigned long long))); CK(cudaMemsetAsync(c->d_icp_prof, 0, 8 * sizeof(unsigned long long), c->stream)); }
 	{
 		int coop = 0, per_sm = 0, sms = 0;
@@ -311,13 +305,11 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	}
 	CK(cudaHostGetDevicePointer(&c->h_out32_dev, c->h_out32, 0));
 	CK(cudaMalloc(&c->d_nupd, NUPD_SLOTS * sizeof(unsigned long long)));
+	CK(cudaMemsetAsync(c->d_nupd, 0, NUPD_SLOTS * sizeof(unsigned long long), c->stream));
 	CK(cudaMalloc(&c->d_dmax, 3 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_dmax, 0, 3 * sizeof(unsigned int), c->stream));
 	c->dmax_slot = -1; c->preprocess_count = 0;
 	{ const char* e = getenv("KFB_INT_ZCHUNK"); c->int_zchunk = e ? (uint32_t) atoi(e) : 0; }
-	c->d_queue = nullptr; c->queue_cap = 0; c->int_launches = 0;
-	c->ray_launches = 0;
-	c->d_tile_cost = nullptr;
 	if (getenv("KFB_RAY_TILECOST")) CK(cudaMalloc(&c->d_tile_cost, (size_t) ((c->cw + 7) / 8) * ((c->ch + 3) / 4) * sizeof(unsigned int)));
 	CK(cudaMalloc(&c->d_tile_ctr, 2 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_tile_ctr, 0, 2 * sizeof(unsigned int), c->stream));
@@ -333,13 +325,58 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	CK(cudaMalloc(&c->d_queue_ctr, 4 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_queue_ctr, 0, 4 * sizeof(unsigned int), c->stream));
 	{
-		int per_sm = 0, sms = 0;
+		int per_sm = 0, per_sm2 = 0, sms = 0;
 		CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
 		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_integrate_run, 256, 0));
+		CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, k_integrate_run2, 256, 0));
 		if (per_sm < 1) per_sm = 1;
+		if (per_sm2 < 1) per_sm2 = 1;
 		const char* e = getenv("KFB_INT_CTAS_PER_SM");
 		if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e);
+		if (e && atoi(e) > 0 && atoi(e) < per_sm2) per_sm2 = atoi(e);
 		c->int_grid = sms * per_sm;
+		c->int_grid2 = sms * per_sm2;
+	}
+	// integrate v2: two (min, max) depth pyramids (they follow the two raw-depth buffers), brick classes of the slab
+	{
+		size_t texels = 0;
+		DepthMip m;
+		memset(&m, 0, sizeof m);
+		uint32_t w = (c->cw + 7) / 8, h = (c->ch + 7) / 8;
+		for (m.n = 0; m.n < MIP_MAX_LEVELS;) {
+			m.w[m.n] = w; m.h[m.n] = h; texels += (size_t) w * h; ++m.n;
+			if (w == 1 && h == 1) break;
+			w = (w + 1) / 2; h = (h + 1) / 2;
+		}
+		for (int b = 0; b < 2; ++b) {
+			CK(cudaMalloc(&c->d_mip[b], texels * sizeof(float2)));
+			c->mip[b] = m;
+			size_t off = 0;
+			for (int l = 0; l < m.n; ++l) { c->mip[b].lvl[l] = c->d_mip[b] + off; off += (size_t) m.w[l] * m.h[l]; }
+			c->mip_valid[b] = false;
+		}
+		CK(cudaMalloc(&c->d_mip_ticket, sizeof(unsigned int)));
+		CK(cudaMemsetAsync(c->d_mip_ticket, 0, sizeof(unsigned int), c->stream));
+		const uint32_t bnx = (cfg->volume_res[0] + 7) / 8, bny = (cfg->volume_res[1] + 7) / 8, bnz = (c->z1 - c->z0 + 7) / 8;
+		if (bnx > 4096 || bny > 4096 || cfg->volume_res[2] > 65535) return set_err(KFB_E_ARG, "volume too large for the integrate work list (x, y <= 32768, z <= 65535)");
+		c->cls_bytes = (size_t) bnx * bny * bnz;
+		CK(cudaMalloc(&c->d_cls, c->cls_bytes));
+		// worst cases: every brick per-voxel (runs of <= 8 layers, two halves per column); FREE and other bricks alternating
+		const size_t worst_mixed = (size_t) bnx * bny * 2 * ((bnz + INT_MIXED_CAP - 1) / INT_MIXED_CAP + 1);
+		CK(cudaMalloc(&c->d_qmixed, worst_mixed * sizeof(uint2)));
+		// checkpoints for a bounded number of items (a surface is 2-D: a frame has far fewer per-voxel bricks than the
+		// worst case; items beyond the capacity replay the additions themselves)
+		{
+			size_t cap = worst_mixed / 8;
+			if (cap < 32768) cap = 32768;
+			if (cap > 524288) cap = 524288;
+			if (cap > worst_mixed) cap = worst_mixed;
+			c->ckpt_cap = (unsigned int) cap;
+			CK(cudaMalloc(&c->d_ckpt, cap * 96 * sizeof(unsigned long long)));
+		}
+		CK(cudaMalloc(&c->d_qfree, (size_t) bnx * bny * ((bnz + 1) / 2 + 1) * sizeof(uint2)));
+		CK(cudaMalloc(&c->d_q2ctr, 8 * sizeof(unsigned int)));
+		CK(cudaMemsetAsync(c->d_q2ctr, 0, 8 * sizeof(unsigned int), c->stream));
 	}
 	// single-slab view by default
 	memset(&c->view_all, 0, sizeof c->view_all);
@@ -350,8 +387,6 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	c->view_all.dx = cfg->volume_dim[0]; c->view_all.dy = cfg->volume_dim[1]; c->view_all.dz = cfg->volume_dim[2];
 	c->view_all.rdx = 1.0f / cfg->volume_dim[0]; c->view_all.rdy = 1.0f / cfg->volume_dim[1]; c->view_all.rdz = 1.0f / cfg->volume_dim[2];
 	c->view_all.fastdiv = (kfb_fastdiv_ok(cfg->volume_dim[0]) && kfb_fastdiv_ok(cfg->volume_dim[1]) && kfb_fastdiv_ok(cfg->volume_dim[2])) ? 1 : 0;
-	for (int i = 0; i < KFB_MAX_SLABS; ++i) c->peer_ptrs[i] = nullptr;
-	memset(&c->brick, 0, sizeof c->brick); c->brick_off = false;
 	const bool whole = (c->z0 == 0 && c->z1 == cfg->volume_res[2]);
 	if ((whole || (c->cfg.flags & KFB_FLAG_BRICKS_MERGED)) && !(c->cfg.flags & KFB_FLAG_RAYCAST_NO_SKIP)) {
 		c->brick.bnx = (cfg->volume_res[0] + 7) / 8; c->brick.bny = (cfg->volume_res[1] + 7) / 8; c->brick.bnz = (cfg->volume_res[2] + 7) / 8;
@@ -361,6 +396,33 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 	int rc = launch_init_volume(c);
 	if (rc) return rc;
 	CK(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
+	if (!cfg || !out) return set_err(KFB_E_ARG, "null argument");
+	*out = nullptr;
+	if (cfg->n_levels < 1 || cfg->n_levels > KFB_MAX_LEVELS)
+		return set_err(KFB_E_ARG, "pyramid levels must be 1..%d (got %d)", KFB_MAX_LEVELS, cfg->n_levels);
+	if (cfg->compute_w == 0 || cfg->compute_h == 0 || cfg->volume_res[0] == 0 || cfg->volume_res[1] == 0 || cfg->volume_res[2] == 0)
+		return set_err(KFB_E_ARG, "empty image or volume");
+	if ((cfg->compute_w >> (cfg->n_levels - 1)) == 0 || (cfg->compute_h >> (cfg->n_levels - 1)) == 0)
+		return set_err(KFB_E_ARG, "image too small for %d pyramid levels", cfg->n_levels);
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return set_err(KFB_E_CUDA, "no CUDA device: libkfb200 has no CPU fallback");
+	if (cfg->device < 0 || cfg->device >= ndev) return set_err(KFB_E_ARG, "device %d out of range (%d devices)", cfg->device, ndev);
+	kfb_ctx* c = new kfb_ctx();   // value-initialised: every pointer / handle below starts out null
+	const int rc = create_impl(cfg, c);
+	if (rc) {
+		// one cleanup path for every failure: kfb_destroy tolerates a partially built context (it must not clobber the message)
+		char keep[sizeof g_err];
+		memcpy(keep, g_err, sizeof keep);
+		kfb_destroy(c);
+		cudaGetLastError();
+		memcpy(g_err, keep, sizeof keep);
+		return rc;
+	}
 	*out = c;
 	return 0;
 }
@@ -368,13 +430,17 @@ int kfb_create(const kfb_config* cfg, kfb_ctx** out) {
 int kfb_destroy(kfb_ctx* c) {
 	if (!c) return 0;
 	cudaSetDevice(c->device);
-	cudaStreamSynchronize(c->stream);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	if (c->side) cudaStreamSynchronize(c->side);
 	for (int i = 0; i < c->n_reg; ++i) cudaHostUnregister((void*) c->reg_ptr[i]);
 	for (int i = 0; i < KFB_MAX_SLABS; ++i) if (c->peer_ptrs[i]) cudaIpcCloseMemHandle(c->peer_ptrs[i]);
-	if (c->brick.flag) cudaFree(c->brick.flag);
+	cudaFree(c->brick.flag);   // cudaFree(nullptr) is a no-op
 	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_fd[0]); cudaFree(c->d_fd[1]);
-	for (int l = 0; l < c->levels; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
-	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax); cudaFree(c->d_queue_ctr); cudaFree(c->d_tile_ctr); if (c->d_tile_cost) cudaFree(c->d_tile_cost); if (c->d_queue) cudaFree(c->d_queue);
+	for (int l = 0; l < KFB_MAX_LEVELS; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
+	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax);
+	cudaFree(c->d_queue_ctr); cudaFree(c->d_tile_ctr); cudaFree(c->d_tile_cost); cudaFree(c->d_queue);
+	cudaFree(c->d_mip[0]); cudaFree(c->d_mip[1]); cudaFree(c->d_mip_ticket); cudaFree(c->d_cls);
+	cudaFree(c->d_qmixed); cudaFree(c->d_qfree); cudaFree(c->d_q2ctr); cudaFree(c->d_ckpt);
 	if (c->d_icp_prof) {
 		unsigned long long h[8];
 		if (cudaMemcpy(h, c->d_icp_prof, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[4])
@@ -382,15 +448,17 @@ int kfb_destroy(kfb_ctx* c) {
 					h[4], h[0] * 1e-3 / h[4], h[1] * 1e-3 / h[4], h[2] * 1e-3 / h[4], h[3] * 1e-3 / h[4]);
 		cudaFree(c->d_icp_prof);
 	}
-	cudaFreeHost(c->h_out32); cudaFree(c->d_bar); cudaFree(c->d_pose);
-	if (c->d_input) cudaFree(c->d_input);
+	if (c->h_out32) cudaFreeHost(c->h_out32);
+	cudaFree(c->d_bar); cudaFree(c->d_pose);
+	cudaFree(c->d_input);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
-	if (c->d_render) cudaFree(c->d_render);
+	cudaFree(c->d_render);
 	timer_free(c->t_pre); timer_free(c->t_track); timer_free(c->t_int); timer_free(c->t_ray);
-	cudaStreamSynchronize(c->side);
-	cudaEventDestroy(c->ev_window); cudaEventDestroy(c->ev_side_done);
-	cudaStreamDestroy(c->side);
-	cudaStreamDestroy(c->stream);
+	if (c->ev_window) cudaEventDestroy(c->ev_window);
+	if (c->ev_side_done) cudaEventDestroy(c->ev_side_done);
+	if (c->side) cudaStreamDestroy(c->side);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	cudaGetLastError();
 	delete c;
 	return 0;
 }
@@ -445,6 +513,10 @@ static int launch_preprocess(kfb_ctx* c, const uint16_t* d_in, uint32_t iw, int 
 	c->fd_cur = nb; c->d_floatDepth = c->d_fd[nb];
 	c->dmax_slot = slot;
 	LAUNCHED(c);
+	// (min, max) pyramid of the new raw depth for integrate's brick classification: same stream, same overlap window
+	k_depth_mip<<<dim3((c->cw + 63) / 64, (c->ch + 63) / 64), 256, 0, stream>>>(c->d_fd[nb], c->cw, c->ch, c->mip[nb], c->d_mip_ticket);
+	c->mip_valid[nb] = true;
+	c->st.kernel_launches++;
 	CK(cudaGetLastError());
 	if (on_side) {
 		int rc = join_side(c);
@@ -719,7 +791,9 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	p.queue_count = c->d_queue_ctr + 2 * qslot; p.queue_head = p.queue_count + 1;
 	p.queue_next = c->d_queue_ctr + 2 * (qslot ^ 1);
 	{
-		const size_t need = (size_t) ((p.sx + 31) / 32) * p.sy;   // one entry per warp-column
+		size_t need = (size_t) ((p.sx + 31) / 32) * p.sy;   // v1: one entry per warp-column; v2: two per brick column
+		const size_t need2 = (size_t) ((p.sx + 7) / 8) * ((p.sy + 7) / 8) * 2;
+		if (need2 > need) need = need2;
 		if (need > c->queue_cap) {
 			if (c->d_queue) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(c->d_queue)); }
 			CK(cudaMalloc(&c->d_queue, need * (sizeof(uint2) + sizeof(unsigned int))));
@@ -729,11 +803,35 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 		p.piece_ctr = reinterpret_cast<unsigned int*>(c->d_queue + c->queue_cap);
 		if (p.zchunk % INT_U != 0 || p.zchunk == 0) return set_err(KFB_E_ARG, "integrate piece length must be a positive multiple of %d", INT_U);
 	}
-	dim3 block(32, 8), grid((p.sx + 31) / 32, (p.sy + 7) / 8);
-	k_integrate_plan<<<grid, block, 0, c->stream>>>(p);
-	LAUNCHED(c);
-	k_integrate_run<<<c->int_grid, 256, 0, c->stream>>>(p);
-	LAUNCHED(c);
+	if (c->cfg.flags & KFB_FLAG_INTEGRATE_V1) {
+		dim3 block(32, 8), grid((p.sx + 31) / 32, (p.sy + 7) / 8);
+		k_integrate_plan<<<grid, block, 0, c->stream>>>(p);
+		LAUNCHED(c);
+		k_integrate_run<<<c->int_grid, 256, 0, c->stream>>>(p);
+		LAUNCHED(c);
+	} else {
+		Integrate2Params q;
+		q.b = p;
+		if (!c->mip_valid[c->fd_cur]) {   // raw depth written from the host (teacher-forced tests): build its pyramid now
+			k_depth_mip<<<dim3((c->cw + 63) / 64, (c->ch + 63) / 64), 256, 0, c->stream>>>(c->d_floatDepth, c->cw, c->ch, c->mip[c->fd_cur], c->d_mip_ticket);
+			LAUNCHED(c);
+			c->mip_valid[c->fd_cur] = true;
+		}
+		q.mip = c->mip[c->fd_cur];
+		q.cls = c->d_cls;
+		q.bnx = (p.sx + 7) / 8; q.bny = (p.sy + 7) / 8;
+		q.maxw_i = (maxweight >= 1.f && maxweight <= 32767.f) ? (int) maxweight : -1;
+		q.vec_ok = (p.sx % 8 == 0) ? 1 : 0;
+		q.std_k = (K[8] == 0.f && K[9] == 0.f && K[10] == 1.f && K[11] == 0.f) ? 1 : 0;
+		q.q_mixed = c->d_qmixed; q.q_free = c->d_qfree;
+		q.ckpt = c->d_ckpt; q.ckpt_cap = c->ckpt_cap;
+		q.ctr = c->d_q2ctr + 4 * qslot; q.ctr_next = c->d_q2ctr + 4 * (qslot ^ 1);
+		dim3 block(32, 8), grid(q.bnx, (q.bny + 7) / 8);
+		k_integrate_plan2<<<grid, block, 0, c->stream>>>(q);
+		LAUNCHED(c);
+		k_integrate_run2<<<c->int_grid2, 256, 0, c->stream>>>(q);
+		LAUNCHED(c);
+	}
 	CK(cudaGetLastError());
 	c->integrate_count++;
 	c->st.frames_integrated++;
@@ -937,6 +1035,7 @@ static int resolve_buffer(kfb_ctx* c, int which, int level, void** ptr, size_t* 
 	case KFB_BUF_RAYTILECOST:
 		if (!c->d_tile_cost) return set_err(KFB_E_STATE, "tile costs are only recorded with KFB_RAY_TILECOST=1");
 		*ptr = c->d_tile_cost; *bytes = (size_t) ((c->cw + 7) / 8) * ((c->ch + 3) / 4) * sizeof(unsigned int); break;
+	case KFB_BUF_BRICKCLASS: *ptr = c->d_cls; *bytes = c->cls_bytes; break;
 	default: return set_err(KFB_E_ARG, "unknown buffer %d", which);
 	}
 	return 0;
@@ -970,7 +1069,7 @@ int kfb_write_buffer(kfb_ctx* c, int which, int level, const void* src, size_t b
 	if (bytes > b) return set_err(KFB_E_ARG, "write of %zu bytes into a %zu-byte buffer", bytes, b);
 	CK(cudaSetDevice(c->device));
 	if (host) { memcpy(p, src, bytes); return 0; }
-	if (which == KFB_BUF_FLOATDEPTH) c->dmax_slot = -1;   // the cached max no longer describes this image
+	if (which == KFB_BUF_FLOATDEPTH) { c->dmax_slot = -1; c->mip_valid[c->fd_cur] = false; }   // the cached max / pyramid no longer describe this image
 	CK(cudaStreamSynchronize(c->stream));
 	CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
 	if (which == KFB_BUF_VOLUME && c->brick.flag) {   // the flags must describe the volume the raycaster will read

@@ -18,6 +18,7 @@ from . import build as _build
 
 KFB_MAX_LEVELS = 8
 FLAG_ICP_HOST_SOLVE = 0x1
+FLAG_INTEGRATE_V1 = 0x4
 FLAG_TRACK_STATUS = 0x2
 FLAG_INTEGRATE_NO_CULL = 0x8
 FLAG_RAYCAST_NO_SKIP = 0x10
@@ -25,7 +26,7 @@ FLAG_BRICKS_MERGED = 0x20
 
 (BUF_VOLUME, BUF_VERTEX, BUF_NORMAL, BUF_FLOATDEPTH, BUF_SCALEDDEPTH, BUF_INVERTEX, BUF_INNORMAL,
  BUF_REDUCTION, BUF_TRACKSTATUS, BUF_RAYCASTPOSE, BUF_OLDPOSE, BUF_GAUSSIAN, BUF_INPUTDEPTH, BUF_REDUCTION_DEV,
- BUF_BRICKFLAGS, BUF_RAYTILECOST) = range(16)
+ BUF_BRICKFLAGS, BUF_RAYTILECOST, BUF_BRICKCLASS) = range(17)
 
 # constant_parameters.h:15-23
 E_DELTA, RADIUS, DIST_THRESHOLD, NORMAL_THRESHOLD, TRACK_THRESHOLD = 0.1, 2, 0.1, 0.8, 0.15
@@ -315,6 +316,7 @@ class Kfusion:
             BUF_REDUCTION_DEV: ((32,), np.float32),
             BUF_BRICKFLAGS: (((vr[2] + 7) // 8, (vr[1] + 7) // 8, (vr[0] + 7) // 8), np.uint8),
             BUF_RAYTILECOST: (((h + 3) // 4, (w + 7) // 8), np.uint32),
+            BUF_BRICKCLASS: (((nz + 7) // 8, (vr[1] + 7) // 8, (vr[0] + 7) // 8), np.uint8),
         }[which]
 
     def read(self, which: int, level: int = 0) -> np.ndarray:

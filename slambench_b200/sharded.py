@@ -34,18 +34,19 @@ from . import kfusion as kf
 
 
 def slab_bounds(n_z: int, world: int, weights=None, align: int = 1) -> list[tuple[int, int]]:
-    """Contiguous z-ranges in rank order.  Without `weights`: sizes differing by at most one slice.  With
+    """Contiguous z-ranges in rank order.  Without `weights`: sizes differing by at most one `align`-slice layer.  With
     per-slice `weights` (expected integrate work, see frustum_slice_weights): boundaries (multiples of `align`)
     that equalise the summed weight, every slab keeping at least `align` slices."""
     if world < 1 or n_z < world * align:
         raise ValueError(f"cannot cut {n_z} slices into {world} slabs")
     if weights is None:
-        base, extra = divmod(n_z, world)
-        out, z = [], 0
+        units = (n_z + align - 1) // align              # whole `align`-slice layers; the last one may be partial
+        base, extra = divmod(units, world)
+        out, u = [], 0
         for r in range(world):
             n = base + (1 if r < extra else 0)
-            out.append((z, z + n))
-            z += n
+            out.append((u * align, min((u + n) * align, n_z)))
+            u += n
         return out
     w = np.asarray(weights, np.float64)
     if w.shape != (n_z,) or not np.all(w >= 0):
@@ -156,7 +157,8 @@ class ShardedKfusion:
             pose0 = kf.identity_pose(ip) if ip.size == 3 else ip.reshape(4, 4)
             vd = float(volumeDimensions) if np.isscalar(volumeDimensions) else float(volumeDimensions[2])
             weights = frustum_slice_weights(vr[2], vd, pose0, balance_k, (int(inputSize[0]), int(inputSize[1])), far=balance_far)
-        self.slabs = slab_bounds(vr[2], world, weights, align=8 if weights is not None else 1)
+        # every slab starts on a brick layer (8 slices): integrate classifies and the raycaster skips per 8^3 brick
+        self.slabs = slab_bounds(vr[2], world, weights, align=8)
         self.bands = row_bands(int(inputSize[1]), world)
         self.pyramid = tuple(int(i) for i in pyramid)
         make = local_factory or (lambda **kw: kf.Kfusion(inputSize, vr, volumeDimensions, initPose, self.pyramid, **kw))

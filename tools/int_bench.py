@@ -27,4 +27,9 @@ with kf.Kfusion((640, 480), vres, 4.8, T0, (10, 5, 4)) as g:
     for _ in range(reps):
         g.integrateKernel(g.inverse(pose), g.cameraMatrix(K), 0.1)
     s = g.stats()
+    if not (int(os.environ.get("KFB_FLAGS", "0"), 0) & 4):
+        cls = g.read(kf.BUF_BRICKCLASS)
+        n = cls.size
+        print(f"  brick classes of the last launch: skip {int((cls == 0).sum())} free {int((cls == 1).sum())} per-voxel {int((cls == 2).sum())} of {n}"
+              f"  -> voxels free {int((cls == 1).sum()) * 512} per-voxel {int((cls == 2).sum()) * 512}")
     print(f"{os.environ.get('KFB_LIB', 'default')}: {vres}^3 integrate {s['ms_integrate'] / reps * 1e3:.1f} us/launch, N_upd {s['voxels_updated_last']}")
