@@ -104,8 +104,9 @@ struct kfb_ctx {
 	float2* d_mip[2]; DepthMip mip[2]; bool mip_valid[2];
 	unsigned int* d_mip_ticket;
 	unsigned char* d_cls; size_t cls_bytes;
-	uint2 *d_qmixed, *d_qfree;           // integrate v2 work items (worst-case sized at create)
-	unsigned int* d_q2ctr;               // 2 slots x {#mixed, #free, next}
+	uint2 *d_qmixed, *d_qfree; uint4* d_qreplay;   // integrate v2 work items (worst-case sized at create)
+	unsigned int* d_q2ctr;               // 2 slots x {#mixed, #free, next, #replay}
+	unsigned int* d_ready;               // [by][bx][half] checkpoint-ready flags (== launch number)
 	unsigned long long* d_ckpt; unsigned int ckpt_cap;   // running-value checkpoints of the MIXED items (768 B each)
 	BrickMap brick;             // brick flags for the raycaster (whole-volume contexts only)
 	bool brick_off;
@@ -375,6 +376,9 @@ static int create_impl(const kfb_config* cfg, kfb_ctx* c) {
 			CK(cudaMalloc(&c->d_ckpt, cap * 96 * sizeof(unsigned long long)));
 		}
 		CK(cudaMalloc(&c->d_qfree, (size_t) bnx * bny * ((bnz + 1) / 2 + 1) * sizeof(uint2)));
+		CK(cudaMalloc(&c->d_qreplay, (size_t) bnx * bny * 2 * ((bnz + 255) / 256) * sizeof(uint4)));
+		CK(cudaMalloc(&c->d_ready, (size_t) bnx * bny * 2 * ((bnz + 255) / 256) * sizeof(unsigned int)));
+		CK(cudaMemsetAsync(c->d_ready, 0, (size_t) bnx * bny * 2 * ((bnz + 255) / 256) * sizeof(unsigned int), c->stream));
 		CK(cudaMalloc(&c->d_q2ctr, 8 * sizeof(unsigned int)));
 		CK(cudaMemsetAsync(c->d_q2ctr, 0, 8 * sizeof(unsigned int), c->stream));
 	}
@@ -440,7 +444,7 @@ int kfb_destroy(kfb_ctx* c) {
 	cudaFree(c->d_status); cudaFree(c->d_partials); cudaFree(c->d_counter); cudaFree(c->d_out32); cudaFree(c->d_nupd); cudaFree(c->d_dmax);
 	cudaFree(c->d_queue_ctr); cudaFree(c->d_tile_ctr); cudaFree(c->d_tile_cost); cudaFree(c->d_queue);
 	cudaFree(c->d_mip[0]); cudaFree(c->d_mip[1]); cudaFree(c->d_mip_ticket); cudaFree(c->d_cls);
-	cudaFree(c->d_qmixed); cudaFree(c->d_qfree); cudaFree(c->d_q2ctr); cudaFree(c->d_ckpt);
+	cudaFree(c->d_qmixed); cudaFree(c->d_qfree); cudaFree(c->d_q2ctr); cudaFree(c->d_ckpt); cudaFree(c->d_qreplay); cudaFree(c->d_ready);
 	if (c->d_icp_prof) {
 		unsigned long long h[8];
 		if (cudaMemcpy(h, c->d_icp_prof, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && h[4])
@@ -823,8 +827,15 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 		q.maxw_i = (maxweight >= 1.f && maxweight <= 32767.f) ? (int) maxweight : -1;
 		q.vec_ok = (p.sx % 8 == 0) ? 1 : 0;
 		q.std_k = (K[8] == 0.f && K[9] == 0.f && K[10] == 1.f && K[11] == 0.f) ? 1 : 0;
+		q.vsz[0] = p.dx / (float) p.sx; q.vsz[1] = p.dy / (float) p.sy; q.vsz[2] = p.dz / (float) p.sz;
+		for (int r = 0; r < 3; ++r)
+			for (int cc = 0; cc < 3; ++cc)
+				q.ca[3 * r + cc] = K[4 * r + 0] * invTrack[cc] + K[4 * r + 1] * invTrack[4 + cc] + K[4 * r + 2] * invTrack[8 + cc];
+		q.tz[0] = invTrack[8]; q.tz[1] = invTrack[9]; q.tz[2] = invTrack[10];
 		q.q_mixed = c->d_qmixed; q.q_free = c->d_qfree;
+		q.q_replay = c->d_qreplay;
 		q.ckpt = c->d_ckpt; q.ckpt_cap = c->ckpt_cap;
+		q.ready = c->d_ready; q.seq = (unsigned int) (c->int_launches & 0xffffffffu);   // already incremented: >= 1
 		q.ctr = c->d_q2ctr + 4 * qslot; q.ctr_next = c->d_q2ctr + 4 * (qslot ^ 1);
 		dim3 block(32, 8), grid(q.bnx, (q.bny + 7) / 8);
 		k_integrate_plan2<<<grid, block, 0, c->stream>>>(q);

@@ -36,7 +36,7 @@
 #ifndef INT_V
 #define INT_V 4   // slices per step of the per-voxel path (divides 8: a step never straddles a brick layer)
 #endif
-static_assert(8 % INT_V == 0, "a step of the per-voxel path stays inside one brick layer");
+static_assert(INT_V == 4, "a step of the per-voxel path is one 8 x 4 x 4 cell");
 
 // ------------------------------------------------------------------------------------------ depth (min, max) mip
 #define MIP_MAX_LEVELS 9
@@ -163,37 +163,41 @@ struct Integrate2Params {
 	int maxw_i;               // floor(maxweight) when the integer weight update is exact (1 <= maxweight <= 32767), else -1
 	int vec_ok;               // sx % 8 == 0: 128-bit voxel accesses are aligned and every x-brick is complete
 	int std_k;                // K's third row is (0, 0, 1, 0): cameraX.z == pos.z bit for bit
-	uint2* q_mixed; uint2* q_free;   // work items (see k_integrate_plan2)
+	// classification geometry, evaluated once per launch on the host (approximate values: the margins cover them)
+	float vsz[3];             // voxel size (m)
+	float ca[9];              // K.rot * invTrack.rot, row-major: camera-space step per metre along the volume's x, y, z
+	float tz[3];              // third row of invTrack.rot: pos.z per metre along x, y, z
+	uint2* q_mixed; uint2* q_free; uint4* q_replay;   // work items (see k_integrate_plan2)
 	unsigned long long* ckpt; // [item][3][32]: the running values (3 packed pairs per column) at the first slice of MIXED item `item`
 	unsigned int ckpt_cap;    // items that have a checkpoint slot; the others replay the additions from z = 0 themselves
-	unsigned int* ctr;        // this launch's [0] #mixed items, [1] #free items, [2] next item to claim
-	unsigned int* ctr_next;   // the other slot's three counters, zeroed by the plan pass for the next launch
+	unsigned int* ready;      // [pass][by][bx][half]: == seq once this launch's checkpoints of that column half are written
+	unsigned int seq;         // launch number (never 0)
+	unsigned int* ctr;        // this launch's [0] #mixed items, [1] #free items, [2] next item to claim, [3] #replay jobs
+	unsigned int* ctr_next;   // the other slot's four counters, zeroed by the plan pass for the next launch
 };
 
-// one brick: class from linear bounds over its box of voxel centres and its 8 projected corners (see the file header)
-__device__ __forceinline__ int classify_brick(const Integrate2Params& q, uint32_t bx, uint32_t by, uint32_t bz, float dmax_all) {
+// Class of the box of voxels [x0, x1] x [y0, y1] x [z0, z1] (inclusive), from linear bounds over the box of their centres
+// and its 8 projected corners (see the file header).  FREE is only claimed where the caller may use it (`allow_free`).
+__device__ __noinline__ int classify_box(const Integrate2Params& q, uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, uint32_t z0, uint32_t z1,
+		float dmax_all, bool allow_free) {
 	const IntegrateParams& p = q.b;
-	const float vx = p.dx / (float) p.sx, vy = p.dy / (float) p.sy, vz = p.dz / (float) p.sz;
-	const uint32_t x0 = bx * 8, y0 = by * 8, z0 = bz * 8;
-	const uint32_t x1 = min(x0 + 7, p.sx - 1), y1 = min(y0 + 7, p.sy - 1), z1 = min(z0 + 7, p.sz - 1);
+	const float vx = q.vsz[0], vy = q.vsz[1], vz = q.vsz[2];
 	// box of the voxel CENTRES (Volume::pos, commons.h:186-189): centre and half extents in metres
 	const float3 ctr = f3(((float) (x0 + x1) * 0.5f + 0.5f) * vx, ((float) (y0 + y1) * 0.5f + 0.5f) * vy, ((float) (z0 + z1) * 0.5f + 0.5f) * vz);
 	const float hx = (float) (x1 - x0) * 0.5f * vx, hy = (float) (y1 - y0) * 0.5f * vy, hz = (float) (z1 - z0) * 0.5f * vz;
 	const Mat4& T = p.invTrack;
-	const Mat4& K = p.K;
 	const float3 pc = mat_point(T, ctr);
-	const float3 cc = mat_point(K, pc);
+	const float3 cc = mat_point(p.K, pc);
 	// camera-space offsets of the three box axes: columns of (K.rot * T.rot) scaled by the half extents
-	const float3 a0 = mat_rotate(K, f3(T.m[0], T.m[4], T.m[8])) * hx, a1 = mat_rotate(K, f3(T.m[1], T.m[5], T.m[9])) * hy,
-			a2 = mat_rotate(K, f3(T.m[2], T.m[6], T.m[10])) * hz;
-	const float hpz = fabsf(T.m[8]) * hx + fabsf(T.m[9]) * hy + fabsf(T.m[10]) * hz;   // half extent of pos.z
+	const float3 a0 = f3(q.ca[0], q.ca[3], q.ca[6]) * hx, a1 = f3(q.ca[1], q.ca[4], q.ca[7]) * hy, a2 = f3(q.ca[2], q.ca[5], q.ca[8]) * hz;
+	const float hpz = fabsf(q.tz[0]) * hx + fabsf(q.tz[1]) * hy + fabsf(q.tz[2]) * hz;   // half extent of pos.z
 	const float hcx = fabsf(a0.x) + fabsf(a1.x) + fabsf(a2.x), hcy = fabsf(a0.y) + fabsf(a1.y) + fabsf(a2.y), hcz = fabsf(a0.z) + fabsf(a1.z) + fabsf(a2.z);
 	// bound on the drift of the reference's accumulated values from the exact line: (N + 64) * 2^-22 times the largest
 	// magnitude along the column (k_integrate_plan uses the same bound); the column spans dz in z
 	const float eps = ((float) p.sz + 64.f) * 2.3841858e-7f;
-	const float3 kz = mat_rotate(K, f3(T.m[2], T.m[6], T.m[10])) * p.dz;   // change of cam over the whole column
-	const float cxm = fabsf(cc.x) + hcx, cym = fabsf(cc.y) + hcy, czm = fabsf(cc.z) + hcz;   // magnitudes inside the brick
-	const float e_pz = eps * (fabsf(pc.z) + hpz + fabsf(T.m[10]) * p.dz);
+	const float3 kz = f3(q.ca[2], q.ca[5], q.ca[8]) * p.dz;   // change of cam over the whole column
+	const float cxm = fabsf(cc.x) + hcx, cym = fabsf(cc.y) + hcy, czm = fabsf(cc.z) + hcz;   // magnitudes inside the box
+	const float e_pz = eps * (fabsf(pc.z) + hpz + fabsf(q.tz[2]) * p.dz);
 	const float e_cx = eps * (cxm + fabsf(kz.x)), e_cy = eps * (cym + fabsf(kz.y)), e_cz = eps * (czm + fabsf(kz.z));
 	const float pz_min = pc.z - hpz - e_pz, pz_max = pc.z + hpz + e_pz;
 	const float cz_min = cc.z - hcz - e_cz, cz_max = cc.z + hcz + e_cz;
@@ -244,18 +248,25 @@ __device__ __forceinline__ int classify_brick(const Integrate2Params& q, uint32_
 	const float slack = p.mu * 1e-5f + 1e-6f * (dr.y + cz_max);
 	if (dr.y + p.mu + slack < cz_min) return CLS_SKIP;                                   // e < -mu everywhere (or depth == 0)
 	const bool inside = pxlo >= 0.f && pxhi <= dwm1 && pylo >= 0.f && pyhi <= dhm1 && pz_min >= 0.000101f;
-	if (inside && q.vec_ok && dr.x - cz_max > p.mu + slack) return CLS_FREE;             // e > mu everywhere, depth > 0
+	if (inside && allow_free && dr.x - cz_max > p.mu + slack) return CLS_FREE;           // e > mu everywhere, depth > 0
 	return inside ? CLS_MIXED_IN : CLS_MIXED_EDGE;
 }
 
-// Work items.  MIXED: { bx | by << 12 | half << 24 | edge << 25, z_first | n_slices << 16 } — at most INT_MIXED_CAP layers of
-// per-voxel bricks in one 8x4-voxel half of a brick column.  FREE: { bx | by << 12, bz_first | n_bricks << 16 }, 1 or 2
-// bricks of one column.  Items are small on purpose: the run kernel's time is the per-warp chain of its longest items.
-// What makes a small MIXED item possible is the CHECKPOINT: the warp that planned the column also replays the reference's
-// additions once per column half, from z = 0, and stores the running values at the first slice of every MIXED item.
+// Work items.
+//   MIXED  { bx | by << 12 | half << 24,  z_first | n_slices << 16 | cells << 24 }: at most INT_MIXED_CAP (<= 2) layers of
+//          per-voxel bricks in one 8x4-voxel half of a brick column.  `cells`: 2 bits per step of 4 slices — the class of
+//          that 8 x 4 x 4 cell of voxels, classified like a brick but on a quarter of its volume: inside a brick that is
+//          MIXED as a whole, about 40 % of the cells are still all-SKIP or all-FREE.
+//   FREE   { bx | by << 12,  bz_first | n_bricks << 16 }: 1 or 2 bricks of one column.
+//   REPLAY { bx | by << 12 | half << 24, first MIXED item, #items, 0 }: one per column half that has MIXED items (they
+//          are contiguous and in z order): the reference's additions (cpp/kernels.cpp:646-647) replayed ONCE from z = 0,
+//          the running values stored as a CHECKPOINT at the first slice of every item.
+// Items are small on purpose: the run kernel's time is the per-warp chain of its longest item, and checkpoints are what
+// makes a small MIXED item possible.
 #ifndef INT_MIXED_CAP
 #define INT_MIXED_CAP 2
 #endif
+static_assert(INT_MIXED_CAP == 1 || INT_MIXED_CAP == 2, "the cell classes of an item take 8 bits: at most 2 layers");
 #define PLAN_GROUPS 8   // 32-layer groups per pass (8 x 32 x 8 = 2048 slices)
 
 // starts of the items inside one 32-layer group: every `cap`-th layer of each run of set bits, counted from the run's start
@@ -271,34 +282,42 @@ __device__ __forceinline__ unsigned int item_len(unsigned int m, uint32_t lane, 
 	return len;
 }
 
-__global__ void __launch_bounds__(256, 3) k_integrate_plan2(Integrate2Params q) {
+__global__ void __launch_bounds__(256, 3) k_integrate_plan2(const __grid_constant__ Integrate2Params q) {
+	__shared__ unsigned int s_mm[8][PLAN_GROUPS], s_ms[8][PLAN_GROUPS];
 	const IntegrateParams& p = q.b;
 	const uint32_t lane = threadIdx.x;
 	const uint32_t bx = blockIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;   // warp-uniform
-	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 3 && threadIdx.y == 0) q.ctr_next[threadIdx.x] = 0u;   // re-arm the other slot
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4 && threadIdx.y == 0) q.ctr_next[threadIdx.x] = 0u;   // re-arm the other slot
 	if (by >= q.bny) return;
 	const uint32_t bz0 = p.z_begin >> 3, bz1 = (p.z_end + 7) >> 3;
 	const bool fast = p.cull && p.mu > 0.f && p.dw <= 2040 && p.dh <= 2040;
 	const float dmax_all = __ldg(q.mip.lvl[q.mip.n - 1]).y;   // the top level is one texel: max over the image
 	const uint32_t halves = (by * 8 + 4 < p.sy) ? 2 : 1;
 	const unsigned int lt = (1u << lane) - 1u;
+	const uint32_t x0 = bx * 8, x1 = min(x0 + 7, p.sx - 1), y0 = by * 8, y1 = min(y0 + 7, p.sy - 1);
+	// the whole column first (most columns lie outside the view frustum: one test instead of one per brick)
+	if (fast && classify_box(q, x0, x1, y0, y1, p.z_begin, p.z_end - 1, dmax_all, false) == CLS_SKIP) {
+		for (uint32_t bz = bz0 + lane; bz < bz1; bz += 32) q.cls[((size_t) (bz - bz0) * q.bny + by) * q.bnx + bx] = CLS_SKIP;
+		return;
+	}
 	for (uint32_t pass0 = bz0; pass0 < bz1; pass0 += 32 * PLAN_GROUPS) {
-		unsigned int mm[PLAN_GROUPS], me[PLAN_GROUPS], ms[PLAN_GROUPS];
+		unsigned int* mm = s_mm[threadIdx.y];   // per group: MIXED layers / first layers of the MIXED items (rolled loops: small code)
+		unsigned int* ms = s_ms[threadIdx.y];
 		unsigned int n_half = 0;
-#pragma unroll
+		// pass 1: classes, FREE items, and the number of MIXED items of the column
+#pragma unroll 1
 		for (int g = 0; g < PLAN_GROUPS; ++g) {
-			mm[g] = me[g] = ms[g] = 0u;
+			if (lane == 0) { mm[g] = 0u; ms[g] = 0u; }
 			if (pass0 + 32 * g >= bz1) continue;   // warp-uniform
 			const uint32_t bz = pass0 + 32 * g + lane;
 			int c = CLS_SKIP;
 			if (bz < bz1) {
-				c = fast ? classify_brick(q, bx, by, bz, dmax_all) : CLS_MIXED_EDGE;
+				c = fast ? classify_box(q, x0, x1, y0, y1, bz * 8, min(bz * 8 + 7, p.sz - 1), dmax_all, q.vec_ok != 0) : CLS_MIXED_EDGE;
 				q.cls[((size_t) (bz - bz0) * q.bny + by) * q.bnx + bx] = (unsigned char) c;
 			}
-			mm[g] = __ballot_sync(0xffffffffu, c >= CLS_MIXED_IN);
-			me[g] = __ballot_sync(0xffffffffu, c == CLS_MIXED_EDGE);
-			ms[g] = item_starts(mm[g], lane, INT_MIXED_CAP);
-			n_half += __popc(ms[g]);
+			const unsigned int m_mixed = __ballot_sync(0xffffffffu, c >= CLS_MIXED_IN), m_starts = item_starts(m_mixed, lane, INT_MIXED_CAP);
+			if (lane == 0) { mm[g] = m_mixed; ms[g] = m_starts; }
+			n_half += __popc(m_starts);
 			// FREE items of this group go out at once (they need no order)
 			const unsigned int mf = __ballot_sync(0xffffffffu, c == CLS_FREE);
 			if (mf) {
@@ -310,49 +329,56 @@ __global__ void __launch_bounds__(256, 3) k_integrate_plan2(Integrate2Params q) 
 			}
 		}
 		if (n_half == 0) continue;
-		// the column's MIXED items take one contiguous range: [half 0's items in z order][half 1's items in z order]
-		unsigned int base_m = 0;
-		if (lane == 0) base_m = atomicAdd(q.ctr + 0, n_half * halves);
+		// the column's MIXED items take one contiguous range, [half 0's items in z order][half 1's items in z order],
+		// and one REPLAY job per half
+		unsigned int base_m = 0, base_r = 0;
+		if (lane == 0) { base_m = atomicAdd(q.ctr + 0, n_half * halves); base_r = atomicAdd(q.ctr + 3, halves); }
 		base_m = __shfl_sync(0xffffffffu, base_m, 0);
+		base_r = __shfl_sync(0xffffffffu, base_r, 0);
+		if (lane < halves) q.q_replay[base_r + lane] = make_uint4(bx | (by << 12) | (lane << 24), base_m + lane * n_half, n_half, 0u);
 		unsigned int at_m = base_m;
-#pragma unroll
+		__syncwarp();
+		// pass 2: the 8 x 4 x 4 cells of the MIXED bricks, and the items
+#pragma unroll 1
 		for (int g = 0; g < PLAN_GROUPS; ++g) {
+			const unsigned int m_mixed = mm[g], m_starts = ms[g];
+			if (m_mixed == 0u) continue;           // warp-uniform
 			const uint32_t bz = pass0 + 32 * g + lane;
-			if ((ms[g] >> lane) & 1u) {
-				const unsigned int len = item_len(mm[g], lane, INT_MIXED_CAP);
-				const unsigned int edge = (me[g] & (((1u << len) - 1u) << lane)) ? 1u : 0u;
-				const uint32_t za = bz * 8, zb = min(p.z_end, (bz + len) * 8);
-				const unsigned int at = at_m + __popc(ms[g] & lt);
-				for (uint32_t h = 0; h < halves; ++h)
-					q.q_mixed[at + h * n_half] = make_uint2(bx | (by << 12) | (h << 24) | (edge << 25), za | ((zb - za) << 16));
-			}
-			at_m += __popc(ms[g]);
-		}
-		// checkpoints: the lanes become the 8 x 4 voxel columns of one half and replay the reference's additions
-		// (cpp/kernels.cpp:646-647) once, from z = 0, past every item start of this column
-		for (uint32_t h = 0; h < halves; ++h) {
-			const uint32_t x = bx * 8 + (lane & 7), y = by * 8 + h * 4 + (lane >> 3);
-			const IntColumn c = int_column(p, x, y);
-			F2 A = f2_make(c.pos0.x, c.pos0.y), B = f2_make(c.pos0.z, c.cam0.x), C = f2_make(c.cam0.y, c.cam0.z);
-			const F2 dA = f2_make(c.delta.x, c.delta.y), dB = f2_make(c.delta.z, c.cameraDelta.x), dC = f2_make(c.cameraDelta.y, c.cameraDelta.z);
-			int z = 0;
-			unsigned int item = base_m + h * n_half;
+			// One cell per lane and round: task t = 4 * (rank of the MIXED brick in this group) + (2 h + s), so a column's
+			// cells are classified side by side instead of four after another by the lane that owns the brick.
+			unsigned int cells = 0;                // bits 2 (2 h + s): class of cell (half h, slices 4 s .. 4 s + 3) of this lane's brick
+			const bool mine = (m_mixed >> lane) & 1u;
+			const unsigned int n_tasks = 4u * (unsigned int) __popc(m_mixed), my_task0 = 4u * (unsigned int) __popc(m_mixed & lt);
+			for (unsigned int r = 0; r * 32u < n_tasks; ++r) {
+				const unsigned int t = r * 32u + lane;
+				int c = CLS_MIXED_EDGE;            // !fast: every cell per voxel, all tests
+				if (t < n_tasks && fast) {
+					const uint32_t tbz = pass0 + 32 * g + __fns(m_mixed, 0, (int) (t >> 2) + 1), hs = t & 3u;
+					const uint32_t cy0 = y0 + 4 * (hs >> 1), cz0 = tbz * 8 + 4 * (hs & 1);
+					c = CLS_SKIP;
+					if (cy0 < p.sy && cz0 < p.z_end) c = classify_box(q, x0, x1, cy0, min(cy0 + 3, p.sy - 1), cz0, min(cz0 + 3, p.sz - 1), dmax_all, true);
+				}
 #pragma unroll
-			for (int g = 0; g < PLAN_GROUPS; ++g) {
-				unsigned int m = ms[g];
-				while (m) {
-					const int za = (int) ((pass0 + 32 * g + (uint32_t) __ffs((int) m) - 1u) * 8);
-					m &= m - 1u;
-#pragma unroll 8
-					for (; z < za; ++z) { A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC); }
-					if (item < q.ckpt_cap) {
-						unsigned long long* o = q.ckpt + (size_t) item * 96 + lane;
-						__stcg(o, A.v); __stcg(o + 32, B.v); __stcg(o + 64, C.v);
-					}
-					++item;
+				for (unsigned int hs = 0; hs < 4; ++hs) {
+					const unsigned int src = my_task0 + hs;
+					const int v = __shfl_sync(0xffffffffu, c, (int) (src & 31u));
+					if (mine && (src >> 5) == r) cells |= (unsigned int) v << (2 * hs);
 				}
 			}
+			const unsigned int next_cells = __shfl_down_sync(0xffffffffu, cells, 1);
+			if ((m_starts >> lane) & 1u) {
+				const unsigned int len = item_len(m_mixed, lane, INT_MIXED_CAP);
+				const uint32_t za = bz * 8, zb = min(p.z_end, (bz + len) * 8);
+				const unsigned int at = at_m + __popc(m_starts & lt);
+				for (uint32_t h = 0; h < halves; ++h) {
+					unsigned int cc = (cells >> (4 * h)) & 0xfu;
+					if (len == 2) cc |= ((next_cells >> (4 * h)) & 0xfu) << 4;
+					q.q_mixed[at + h * n_half] = make_uint2(bx | (by << 12) | (h << 24), za | ((zb - za) << 16) | (cc << 24));
+				}
+			}
+			at_m += __popc(m_starts);
 		}
+		__syncwarp();
 	}
 }
 
@@ -382,6 +408,37 @@ __device__ __forceinline__ uint32_t tsdf_update_free(uint32_t v, float maxweight
 	return tsdf_update_free_slow(v, maxweight, rcp);
 }
 
+// flag of the REPLAY job that covers slice `za` of column half (bx, by, half): one job per plan pass of 32 * PLAN_GROUPS layers
+__device__ __forceinline__ size_t ready_index(const Integrate2Params& q, uint32_t bx, uint32_t by, uint32_t half, uint32_t za) {
+	const uint32_t pass = ((za >> 3) - (q.b.z_begin >> 3)) / (32u * PLAN_GROUPS);
+	return (((size_t) pass * q.bny + by) * q.bnx + bx) * 2 + half;
+}
+
+// REPLAY job: the lanes are the 8 x 4 voxel columns of one column half; one sweep from z = 0 past every item start
+__device__ __forceinline__ void integrate_replay_job(const Integrate2Params& q, uint4 job, uint32_t lane) {
+	const IntegrateParams& p = q.b;
+	const uint32_t bx = job.x & 0xfffu, by = (job.x >> 12) & 0xfffu, half = (job.x >> 24) & 1u;
+	const uint32_t x = bx * 8 + (lane & 7), y = by * 8 + half * 4 + (lane >> 3);
+	const IntColumn c = int_column(p, x, y);
+	// running values, packed in pairs: (pos.x, pos.y) (pos.z, cam.x) (cam.y, cam.z)
+	F2 A = f2_make(c.pos0.x, c.pos0.y), B = f2_make(c.pos0.z, c.cam0.x), C = f2_make(c.cam0.y, c.cam0.z);
+	const F2 dA = f2_make(c.delta.x, c.delta.y), dB = f2_make(c.delta.z, c.cameraDelta.x), dC = f2_make(c.cameraDelta.y, c.cameraDelta.z);
+	int z = 0;
+	for (unsigned int k = 0; k < job.z; ++k) {
+		const unsigned int item = job.y + k;
+		const int za = (int) (__ldcg(&q.q_mixed[item].y) & 0xffffu);
+#pragma unroll 8
+		for (; z < za; ++z) { A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC); }
+		if (item < q.ckpt_cap) {
+			unsigned long long* o = q.ckpt + (size_t) item * 96 + lane;
+			__stcg(o, A.v); __stcg(o + 32, B.v); __stcg(o + 64, C.v);
+		}
+	}
+	__threadfence();
+	__syncwarp();
+	if (lane == 0) st_release_u32(q.ready + ready_index(q, bx, by, half, __ldcg(&q.q_mixed[job.y].y) & 0xffffu), q.seq);
+}
+
 __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integrate2Params q) {
 	__shared__ float rcp[128];
 	const IntegrateParams& p = q.b;
@@ -395,21 +452,30 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 	const float* __restrict__ depth = p.depth;
 	const uint32_t dw = p.dw;
 	const size_t plane = (size_t) p.sx * p.sy;
-	const unsigned int n_mixed = __ldcg(q.ctr + 0), n_free = __ldcg(q.ctr + 1), n_items = n_mixed + n_free;
+	const unsigned int n_mixed = __ldcg(q.ctr + 0), n_free = __ldcg(q.ctr + 1), n_replay = __ldcg(q.ctr + 3);
+	const unsigned int n_items = n_replay + n_mixed + n_free;
+	// claim order: all REPLAY jobs (long serial chains: started first), then the FREE items (pure memory streaming: the warps
+	// that got no job stream while the jobs run, so no MIXED item ever waits for its checkpoint), then the MIXED items
 	unsigned int updated = 0;
 
-	// Items are taken in an order that interleaves the two queues in proportion: the FREE items are pure memory streaming,
-	// the MIXED ones latency / issue bound; together on an SM they overlap.
+	// one claim ahead: the atomic's round trip to the single hot counter (~1-2 us with 4700 warps on it) hides behind the
+	// current item; items are small, so the item a warp holds in reserve costs the tail little
+	unsigned int nxt = 0;
+	if (lane == 0) nxt = atomicAdd(q.ctr + 2, 1u);
 	for (;;) {
-		unsigned int it = 0;
-		if (lane == 0) it = atomicAdd(q.ctr + 2, 1u);
-		it = __shfl_sync(0xffffffffu, it, 0);
+		unsigned int it = __shfl_sync(0xffffffffu, nxt, 0);
 		if (it >= n_items) break;
-		const unsigned int free_before = (unsigned int) (((unsigned long long) it * n_free) / n_items);
-		const bool is_free = (unsigned int) (((unsigned long long) (it + 1) * n_free) / n_items) != free_before;
+		if (lane == 0) nxt = atomicAdd(q.ctr + 2, 1u);
+		if (it < n_replay) {
+			integrate_replay_job(q, __ldcg(q.q_replay + it), lane);
+			continue;
+		}
+		it -= n_replay;
+		const bool is_free = it < n_free;
+		const unsigned int idx = is_free ? it : it - n_free;
 		if (is_free) {
 			// ---------------- FREE item: 1 or 2 bricks (bx, by, bz ..): per instruction 2 slices x 8 rows x 2 half-rows of 4 voxels
-			const uint2 item = __ldcg(q.q_free + free_before);
+			const uint2 item = __ldcg(q.q_free + idx);
 			const uint32_t bx = item.x & 0xfffu, by = (item.x >> 12) & 0xfffu;
 			const uint32_t z0 = (item.y & 0xffffu) * 8, z1 = min(p.z_end, z0 + (item.y >> 16) * 8);
 			const uint32_t yy = by * 8 + ((lane >> 1) & 7);
@@ -445,34 +511,48 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 			}
 			continue;
 		}
-		// ---------------- MIXED item: 8 x 4 columns, slices [za, zb)
-		const uint2 item = __ldcg(q.q_mixed + (it - free_before));
+		// ---------------- MIXED item: 8 x 4 columns, slices [za, zb), one class per step of 4 slices
+		const uint2 item = __ldcg(q.q_mixed + idx);
+		const unsigned int cells = item.y >> 24;
+		if (cells == 0u) continue;   // every cell of this half is SKIP
 		const uint32_t bx = item.x & 0xfffu, by = (item.x >> 12) & 0xfffu, half = (item.x >> 24) & 1u;
-		const bool edge = (item.x >> 25) & 1u;
 		const uint32_t x = bx * 8 + (lane & 7), y = by * 8 + half * 4 + (lane >> 3);
-		const int za = (int) (item.y & 0xffffu), zb = za + (int) (item.y >> 16);
+		const int za = (int) (item.y & 0xffffu), zb = za + (int) ((item.y >> 16) & 0xffu);
 		const bool valid = x < p.sx && y < p.sy;
-		// The tile's voxels are pulled into L2 a brick layer ahead of their use (one 32-byte sector = 8 voxels in x per lane
-		// and instruction: lane -> row lane >> 3, slice lane & 7), so the read-modify-write below never waits for DRAM.
-		// Sectors of voxels that turn out not to be updated are fetched in vain (~40 % of a per-voxel brick).
-		const short2* pf = p.vol + (size_t) (bx * 8) + (size_t) (by * 8 + half * 4 + (lane >> 3)) * p.sx;
-		const bool pf_row = by * 8 + half * 4 + (lane >> 3) < p.sy;
-		auto prefetch_layer = [&](int zl) {   // slices zl .. zl + 7
-			const int zz = zl + (int) (lane & 7);
-			if (pf_row && zz < zb) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t) ((uint32_t) zz - p.z_begin) * plane));
-		};
-		prefetch_layer(za);
-		prefetch_layer(za + 8);
-		// running values, packed in pairs: (pos.x, pos.y) (pos.z, cam.x) (cam.y, cam.z), at slice za: from the plan pass's
-		// checkpoint, or (more items than checkpoint slots) by replaying the reference's additions from z = 0 here
+		// The tile's voxels are pulled into L2 ahead of their use (one 32-byte sector = 8 voxels in x per lane and
+		// instruction: lane -> row lane >> 3, slice lane & 7), so the read-modify-write below does not wait for DRAM.
+		// Sectors of voxels that turn out not to be updated are fetched in vain.
+		{
+			const short2* pf = p.vol + (size_t) (bx * 8) + (size_t) (by * 8 + half * 4 + (lane >> 3)) * p.sx;
+			const bool pf_row = by * 8 + half * 4 + (lane >> 3) < p.sy;
+#pragma unroll
+			for (int l = 0; l < INT_MIXED_CAP; ++l) {
+				const int zz = za + 8 * l + (int) (lane & 7);
+				if (pf_row && zz < zb && ((cells >> (4 * l + 2 * ((lane & 7) >> 2))) & 3u))
+					asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + (size_t) ((uint32_t) zz - p.z_begin) * plane));
+			}
+		}
+		// running values, packed in pairs: (pos.x, pos.y) (pos.z, cam.x) (cam.y, cam.z), at slice za: from the REPLAY job's
+		// checkpoint, or (more items than checkpoint slots / the job is not done after a long wait) by replaying the
+		// reference's additions from z = 0 here
 		F2 A, B, C, dA, dB, dC;
 		{
 			const float3 delta = mat_rotate(p.invTrack, f3(0, 0, p.dz / (float) p.sz)), cameraDelta = mat_rotate(p.K, delta);
 			dA = f2_make(delta.x, delta.y); dB = f2_make(delta.z, cameraDelta.x); dC = f2_make(cameraDelta.y, cameraDelta.z);
 		}
-		const unsigned int mi = it - free_before;
-		if (mi < q.ckpt_cap) {
-			const unsigned long long* o = q.ckpt + (size_t) mi * 96 + lane;
+		bool have = false;
+		if (idx < q.ckpt_cap) {
+			// The job was claimed before this item (queue order) by a warp that is running and never waits: the flag WILL
+			// flip.  The poll is bounded anyway — a warp that gives up just does the replay itself.
+			const unsigned int* flag = q.ready + ready_index(q, bx, by, half, (uint32_t) za);
+			for (int spin = 0; spin < 4096; ++spin) {
+				if (ld_acquire_u32(flag) == q.seq) { have = true; break; }
+				__nanosleep(200);
+			}
+			have = __all_sync(0xffffffffu, have);
+		}
+		if (have) {
+			const unsigned long long* o = q.ckpt + (size_t) idx * 96 + lane;
 			A.v = __ldcg(o); B.v = __ldcg(o + 32); C.v = __ldcg(o + 64);
 		} else {
 			const IntColumn c = int_column(p, x, y);
@@ -485,35 +565,49 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 		// loads back to back, then the updates and stores.
 #pragma unroll 1
 		for (int z = za; z < zb; z += INT_V, col += INT_V * plane) {
-			if (((z - za) & 7) == 0) prefetch_layer(z + 16);
+			const unsigned int cls = (cells >> (2 * ((z - za) >> 2))) & 3u;   // warp-uniform
+			if (cls == CLS_SKIP) {
+#pragma unroll
+				for (int u = 0; u < INT_V; ++u) { A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC); }
+				continue;
+			}
+			const bool edge = cls == CLS_MIXED_EDGE;
 			float sdf[INT_V];
 			short2 v[INT_V];
 			unsigned int low = 0;   // bit u: this lane stored a tsdf below BRICK_T in slice z + u
+			if (cls == CLS_FREE) {
 #pragma unroll
-			for (int u = 0; u < INT_V; ++u) {
-				const float Px = f2_lo(A), Py = f2_hi(A), Pz = f2_lo(B), Cx = f2_hi(B), Cy = f2_lo(C), Cz = f2_hi(C);
-				A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC);
-				bool act = valid && (z + u < zb);
-				if (edge) act = act && !(Pz < 0.0001f);
-				float s = -4.f;   // "no update" (a real sdf is > -1)
-				if (fast) {
-					const float r = rcp_approx(Cz);
-					const float pxf = Cx * r + 0.5f, pyf = Cy * r + 0.5f;
-					// the truncated pixel and the bounds tests (against the integers 0, w-1, h-1) can only differ from
-					// the exact ones when the value is within `tol` of an integer.  NaN/inf fail both comparisons.
-					const bool sure = (fabsf(pxf - rintf(pxf)) >= tol) && (fabsf(pyf - rintf(pyf)) >= tol);
-					bool inb = true;
-					if (edge) inb = !(pxf < 0 || pxf > dwm1 || pyf < 0 || pyf > dhm1);
-					const uint32_t idx = inb ? ((uint32_t) pxf + (uint32_t) pyf * dw) : 0u;
-					const float d = __ldg(depth + idx);
-					const float e_ = d - Cz;
-					// sure & inside: e > mu => sdf == 1 exactly; e < -mu or d == 0 => no update;
-					// sure & outside: no update; |e| <= mu: the reference's sqrt/division expression; not sure: all of it
-					if (act && sure && inb && e_ > mu && d != 0) s = 1.f;
-					if (act && sure && inb && d != 0 && !(e_ > mu) && !(e_ < -mu)) s = integrate_exact_sdf(Px, Py, Pz, e_, mu);
-					if (act && !sure) s = integrate_exact(Px, Py, Pz, Cx, Cy, Cz, depth, dw, dwm1, dhm1, mu);
-				} else if (act) s = integrate_exact(Px, Py, Pz, Cx, Cy, Cz, depth, dw, dwm1, dhm1, mu);
-				sdf[u] = s;
+				for (int u = 0; u < INT_V; ++u) {
+					A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC);
+					sdf[u] = (valid && (z + u < zb)) ? 1.f : -4.f;
+				}
+			} else {
+#pragma unroll
+				for (int u = 0; u < INT_V; ++u) {
+					const float Px = f2_lo(A), Py = f2_hi(A), Pz = f2_lo(B), Cx = f2_hi(B), Cy = f2_lo(C), Cz = f2_hi(C);
+					A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC);
+					bool act = valid && (z + u < zb);
+					if (edge) act = act && !(Pz < 0.0001f);
+					float s = -4.f;   // "no update" (a real sdf is > -1)
+					if (fast) {
+						const float r = rcp_approx(Cz);
+						const float pxf = Cx * r + 0.5f, pyf = Cy * r + 0.5f;
+						// the truncated pixel and the bounds tests (against the integers 0, w-1, h-1) can only differ from
+						// the exact ones when the value is within `tol` of an integer.  NaN/inf fail both comparisons.
+						const bool sure = (fabsf(pxf - rintf(pxf)) >= tol) && (fabsf(pyf - rintf(pyf)) >= tol);
+						bool inb = true;
+						if (edge) inb = !(pxf < 0 || pxf > dwm1 || pyf < 0 || pyf > dhm1);
+						const uint32_t pix = inb ? ((uint32_t) pxf + (uint32_t) pyf * dw) : 0u;
+						const float d = __ldg(depth + pix);
+						const float e_ = d - Cz;
+						// sure & inside: e > mu => sdf == 1 exactly; e < -mu or d == 0 => no update;
+						// sure & outside: no update; |e| <= mu: the reference's sqrt/division expression; not sure: all of it
+						if (act && sure && inb && e_ > mu && d != 0) s = 1.f;
+						if (act && sure && inb && d != 0 && !(e_ > mu) && !(e_ < -mu)) s = integrate_exact_sdf(Px, Py, Pz, e_, mu);
+						if (act && !sure) s = integrate_exact(Px, Py, Pz, Cx, Cy, Cz, depth, dw, dwm1, dhm1, mu);
+					} else if (act) s = integrate_exact(Px, Py, Pz, Cx, Cy, Cz, depth, dw, dwm1, dhm1, mu);
+					sdf[u] = s;
+				}
 			}
 #pragma unroll
 			for (int u = 0; u < INT_V; ++u)
