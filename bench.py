@@ -5,8 +5,8 @@ raycast) on B200, through the C ABI of libkfb200.so (include/kfb200.h).
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--volume 512]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A STEP is one 640x480 depth frame through the whole pipeline, driven exactly like
-kfusion/src/benchmark.cpp:125-150 drives `Kfusion`.  The workload is BASELINE.json configs[1]:
+A STEP is one 640x480 depth frame through the whole pipeline: one `Kfusion::computeFrame` call
+(kernels.h:158-166; `--staged`: the four stage calls exactly as kfusion/src/benchmark.cpp:125-150 issues them).  The workload is BASELINE.json configs[1]:
 the synthetic analytic-room sequence, 512^3 volume, 4.8 m, mu 0.1, pyramid 10,5,4, -r 1 -t 1.
 With W >= 4 the warm-up covers the reference's start-up frames 0-3 (untracked by construction,
 SURVEY §8a a18), so every timed frame is tracked + integrated + raycast.
@@ -258,14 +258,19 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
             def frame(f):
-                if not resident and args.compute_frame:
-                    # the reference's one-call entry point (Kfusion::computeFrame, kernels.h:158-166): same four stages
-                    g.computeFrame(depth_np[f], None, K, 1, 1, ICP_THRESHOLD, MU, f)
+                if not args.staged:
+                    # the reference's one-call entry point (Kfusion::computeFrame, kernels.h:158-166): the library enqueues
+                    # all four stages before it waits for the pose; tracked / integrated / pose are read back every frame
+                    if resident:
+                        g.computeFrame_device(dev[f].data_ptr(), (W_IMG, H_IMG), K, 1, 1, ICP_THRESHOLD, MU, f)
+                    else:
+                        g.computeFrame(depth_np[f], None, K, 1, 1, ICP_THRESHOLD, MU, f)   # numpy view of the pinned tensor's memory
                     return g.getTracked(), g.getIntegrated(), g.getPose()
+                # the four stage calls, exactly as benchmark.cpp:125-150 issues them
                 if resident:
                     g.preprocessing_device(dev[f].data_ptr(), (W_IMG, H_IMG))
                 else:
-                    g.preprocessing(depth_np[f])          # numpy view of the pinned tensor's memory
+                    g.preprocessing(depth_np[f])
                 tr = g.tracking(K, ICP_THRESHOLD, 1, f)
                 it = g.integration(K, 1, MU, f)
                 g.raycasting(K, MU, f)
@@ -511,7 +516,8 @@ def sharded_run(args, rank: int, world: int, local_rank: int, torch, dist, volum
                 "warmup": warmup, "ms_per_step": ms_all / steps, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": workload_name(volume), "volume": volume, "frames": n,
-                           "parallelism": f"z-slab x{world}: integrate local, raycast via NVLink peer slabs + NCCL all-gather, ICP {args.icp_mode}",
+                           "parallelism": f"z-slab x{world}: integrate local, raycast via NVLink peer slabs, map bands + brick flags stored into the "
+                                          f"peers, peer-memory barriers ({s.transport} transport), ICP {args.icp_mode}",
                            "slabs": [list(z) for z in s.slabs],
                            "tracked_frames": int(tracked), "final_pose_err_m": err},
                 "e2e": {"value": steps / (ms_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W_IMG * H_IMG * 2,
@@ -521,7 +527,7 @@ def sharded_run(args, rank: int, world: int, local_rank: int, torch, dist, volum
                              "frac": alg / t_int / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src + f" x{world}",
                              "us_per_launch": t_int * 1e6},
                 "stage_ms_per_frame": {"preprocess": float(tstage[0]), "track": float(tstage[1]),
-                                       "integrate+flag merge": float(tstage[2]), "raycast+all-gather": float(tstage[3]),
+                                       "integrate+barrier": float(tstage[2]), "raycast+band exchange": float(tstage[3]),
                                        "note": "synchronised after every stage, max over ranks"},
             }
             return line
@@ -537,8 +543,9 @@ def main():
     ap.add_argument("--volume", type=int, default=512, help="volume resolution N (N^3 voxels); default = BASELINE configs[1]")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--compute-frame", action="store_true",
-                    help="e2e arm: one Kfusion::computeFrame call per frame instead of the four stage calls of benchmark.cpp")
+    ap.add_argument("--staged", action="store_true",
+                    help="drive the four stage calls of benchmark.cpp (preprocessing / tracking / integration / raycasting) instead of "
+                         "one Kfusion::computeFrame call per frame")
     ap.add_argument("--no-breakdown", action="store_true", help="skip the extra per-stage timing pass")
     ap.add_argument("--mode", default="sequences", choices=["sequences", "sharded"],
                     help="N > 1: one independent sequence per GPU (weak scaling, default) or ONE sequence on a z-slab sharded volume (strong)")

@@ -107,8 +107,16 @@ int kfb_track(kfb_ctx* ctx, const float k[4], float icp_threshold, uint32_t trac
 int kfb_integrate(kfb_ctx* ctx, const float k[4], uint32_t integration_rate, float mu, uint32_t frame, int* integrated);
 /* Kfusion::raycasting(float4 k, float mu, uint frame)   cpp/kernels.cpp:973-986 (the reference always returns false) */
 int kfb_raycast(kfb_ctx* ctx, const float k[4], float mu, uint32_t frame);
-/* Kfusion::computeFrame(...)                            cpp/kernels.cpp:1048-1055 */
+/* Kfusion::computeFrame(...)                            cpp/kernels.cpp:1048-1055.  The one entry point that knows the whole
+ * frame up front: all four stages are enqueued before the host waits for anything (checkPose, inverse(pose) and
+ * raycastPose * invK run in the ICP kernel's last CTA); it returns when pose / tracked / integrated are known, while
+ * integrate and raycast may still be running.  KFB_NO_ASYNC=1 forces the staged calls instead (A/B). */
 int kfb_compute_frame(kfb_ctx* ctx, const uint16_t* depth_mm, uint32_t in_w, uint32_t in_h, const float k[4],
+		uint32_t integration_rate, uint32_t tracking_rate, float icp_threshold, float mu, uint32_t frame,
+		int* tracked, int* integrated);
+
+/* same, with the sensor frame already resident in device memory (bench.py's HBM-resident arm) */
+int kfb_compute_frame_device(kfb_ctx* ctx, const uint16_t* dev_depth_mm, uint32_t in_w, uint32_t in_h, const float k[4],
 		uint32_t integration_rate, uint32_t tracking_rate, float icp_threshold, float mu, uint32_t frame,
 		int* tracked, int* integrated);
 
@@ -172,6 +180,23 @@ int kfb_stream(kfb_ctx* ctx, void** stream);
 int kfb_slab_ipc_handle(kfb_ctx* ctx, uint8_t handle64[64]);
 /* import the peers' slabs: handles[r] / z_begin[r] for r in [0, world); own rank's entry is ignored */
 int kfb_slab_import(kfb_ctx* ctx, int rank, int world, const uint8_t* handles64, const uint32_t* z_begin);
+/* The same over PEER MEMORY only (no NCCL on the data path): besides its slab, every context exports its raycast maps, its
+ * brick-flag map and a barrier slot.  After kfb_ipc_import a context
+ *   - stores the brick flags of its slab into every peer's map while it integrates (nothing to merge afterwards),
+ *   - stores its band of the raycast vertex / normal maps into every peer's maps (the all-gather, fused into k_raycast),
+ *   - ends kfb_integrate and kfb_raycast with a stream-ordered barrier over the group (kfb_peer_barrier),
+ * so a host only has to move the 64-byte handles between its processes once (files, pipes, MPI, torch.distributed ...)
+ * and then drives every rank with the ordinary stage calls.  All ranks must issue the same calls in the same order. */
+typedef struct kfb_ipc_handles {
+	uint8_t volume[64], vertex[64], normal[64], bricks[64], sync[64];
+	uint32_t has_bricks;          /* 0: this context keeps no brick flags (KFB_FLAG_RAYCAST_NO_SKIP) */
+	uint32_t slab_z0, slab_z1;    /* the slab the handles belong to */
+	uint32_t reserved;
+} kfb_ipc_handles;
+int kfb_ipc_export(kfb_ctx* ctx, kfb_ipc_handles* out);
+int kfb_ipc_import(kfb_ctx* ctx, int rank, int world, const kfb_ipc_handles* all /* [world], rank order */);
+/* stream-ordered barrier over the group (needed explicitly only around the stage-level kfb_k_* calls) */
+int kfb_peer_barrier(kfb_ctx* ctx);
 /* rows [row0, row1) of the computation image this context is responsible for in kfb_raycast / kfb_k_raycast and in
  * the stage-level kfb_k_track_reduce (level l uses [row0 >> l, row1 >> l)); (0, 0) = the whole image.  The host
  * harness all-gathers the raycast bands and all-reduces the 32 partial sums (KFB_BUF_REDUCTION_DEV) over NCCL. */

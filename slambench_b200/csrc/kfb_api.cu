@@ -92,6 +92,9 @@ struct kfb_ctx {
 	float* h_out32;             // mapped pinned: [0..31] result, [32] seq flag, [48..63] pose, [64] iterations
 	unsigned int* d_bar;        // k_icp grid barrier: [0] arrivals, [1] generation, [2] converged
 	float* d_pose;              // k_icp: current pose [16]
+	DevFrame* d_frame;          // frame state written by k_icp's tail (kfb_compute_frame's whole-frame enqueue)
+	bool no_async;              // KFB_NO_ASYNC=1: kfb_compute_frame always takes the staged path (A/B)
+	cudaEvent_t ev_h2d; bool ev_h2d_pending;   // the last asynchronous copy out of a caller's buffer
 	int icp_grid;               // co-resident CTAs for the cooperative launch
 	unsigned long long* d_icp_prof;   // phase timers, only with KFB_ICP_PROFILE=1
 	float* h_out32_dev;
@@ -125,6 +128,12 @@ struct kfb_ctx {
 	int rank, world;
 	VolView view_all;           // slab table for raycast
 	void* peer_ptrs[KFB_MAX_SLABS];
+	// z-slab mode over peer memory (kfb_ipc_import): peers' maps, flag maps and barrier slots, opened through CUDA IPC
+	bool peer_mode;
+	void* peer_open[KFB_MAX_SLABS][4];      // vertex, normal, bricks, sync of rank r (to close)
+	float* peer_vertex[KFB_MAX_SLABS]; float* peer_normal[KFB_MAX_SLABS]; unsigned char* peer_bricks[KFB_MAX_SLABS];
+	PeerSync* d_sync; PeerSyncTable sync_all;
+	unsigned int barrier_count;
 	uint32_t band0, band1;      // pixel rows handled by this context (multi-GPU); whole image by default
 	// registered host pointers (benchmark.cpp reuses one malloc'd frame buffer)
 	const void* reg_ptr[4]; size_t reg_bytes[4]; int n_reg;
@@ -292,6 +301,13 @@ static int create_impl(const kfb_config* cfg, kfb_ctx* c) {
 	CK(cudaMalloc(&c->d_bar, 4 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_bar, 0, 4 * sizeof(unsigned int), c->stream));
 	CK(cudaMalloc(&c->d_pose, 16 * sizeof(float)));
+	CK(cudaMalloc(&c->d_sync, sizeof(PeerSync)));
+	CK(cudaMemsetAsync(c->d_sync, 0, sizeof(PeerSync), c->stream));
+	CK(cudaMalloc(&c->d_frame, sizeof(DevFrame)));
+	CK(cudaMemsetAsync(c->d_frame, 0, sizeof(DevFrame), c->stream));
+	{ const char* e = getenv("KFB_NO_ASYNC"); c->no_async = e && atoi(e) > 0; }
+	CK(cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming));
+	c->ev_h2d_pending = false;
 	if (getenv("KFB_ICP_PROFILE")) { CK(cudaMalloc(&c->d_icp_prof, 8 * sizeof(unsigned long long))); CK(cudaMemsetAsync(c->d_icp_prof, 0, 8 * sizeof(unsigned long long), c->stream)); }
 	{
 		int coop = 0, per_sm = 0, sms = 0;
@@ -438,6 +454,9 @@ int kfb_destroy(kfb_ctx* c) {
 	if (c->side) cudaStreamSynchronize(c->side);
 	for (int i = 0; i < c->n_reg; ++i) cudaHostUnregister((void*) c->reg_ptr[i]);
 	for (int i = 0; i < KFB_MAX_SLABS; ++i) if (c->peer_ptrs[i]) cudaIpcCloseMemHandle(c->peer_ptrs[i]);
+	for (int i = 0; i < KFB_MAX_SLABS; ++i)
+		for (int j = 0; j < 4; ++j) if (c->peer_open[i][j]) cudaIpcCloseMemHandle(c->peer_open[i][j]);
+	cudaFree(c->d_sync);
 	cudaFree(c->brick.flag);   // cudaFree(nullptr) is a no-op
 	cudaFree(c->d_vol); cudaFree(c->d_vertex); cudaFree(c->d_normal); cudaFree(c->d_fd[0]); cudaFree(c->d_fd[1]);
 	for (int l = 0; l < KFB_MAX_LEVELS; ++l) { cudaFree(c->d_scaled[l]); cudaFree(c->d_inV[l]); cudaFree(c->d_inN[l]); }
@@ -453,7 +472,8 @@ int kfb_destroy(kfb_ctx* c) {
 		cudaFree(c->d_icp_prof);
 	}
 	if (c->h_out32) cudaFreeHost(c->h_out32);
-	cudaFree(c->d_bar); cudaFree(c->d_pose);
+	cudaFree(c->d_bar); cudaFree(c->d_pose); cudaFree(c->d_frame);
+	if (c->ev_h2d) cudaEventDestroy(c->ev_h2d);
 	cudaFree(c->d_input);
 	if (c->h_stage) cudaFreeHost(c->h_stage);
 	cudaFree(c->d_render);
@@ -476,6 +496,8 @@ int kfb_reset(kfb_ctx* c) {
 int kfb_sync(kfb_ctx* c) {
 	if (!c) return set_err(KFB_E_ARG, "null ctx");
 	CK(cudaStreamSynchronize(c->stream));
+	const unsigned int e = *(volatile unsigned int*) (c->h_out32 + 34);
+	if (e) { *(volatile unsigned int*) (c->h_out32 + 34) = 0; return set_err(KFB_E_STATE, "z-slab barrier timed out waiting for rank %u", e - 0x100u); }
 	return 0;
 }
 int kfb_stream(kfb_ctx* c, void** s) { *s = (void*) c->stream; return 0; }
@@ -565,6 +587,8 @@ int kfb_preprocess(kfb_ctx* c, const uint16_t* depth, uint32_t iw, uint32_t ih) 
 	if (pinned) {
 		ps = preprocess_stream(c, &on_side);
 		CK(cudaMemcpyAsync(c->d_input, depth, bytes, cudaMemcpyHostToDevice, ps));
+		CK(cudaEventRecord(c->ev_h2d, ps));
+		c->ev_h2d_pending = true;
 	} else {
 		if (c->stage_bytes < bytes) {
 			if (c->h_stage) CK(cudaFreeHost(c->h_stage));
@@ -599,10 +623,11 @@ static int launch_pyramid(kfb_ctx* c, const float k[4]) {
 	PyrParams p;
 	memset(&p, 0, sizeof p);
 	p.d0 = c->d_scaled[0];
-	p.levels = c->levels;
+	const int fused = c->levels < 3 ? c->levels : 3;   // k_pyramid recomputes levels 1, 2 from level 0; deeper levels chain
+	p.levels = fused;
 	p.e_d = c_e_delta * 3;
 	uint32_t first = 0;
-	for (int l = 0; l < c->levels; ++l) {
+	for (int l = 0; l < fused; ++l) {
 		p.depth[l] = c->d_scaled[l]; p.vertex[l] = c->d_inV[l]; p.normal[l] = c->d_inN[l];
 		p.w[l] = c->lw[l]; p.h[l] = c->lh[l];
 		p.first[l] = first;
@@ -612,11 +637,21 @@ static int launch_pyramid(kfb_ctx* c, const float k[4]) {
 		const float ks[4] = { k[0] / s, k[1] / s, k[2] / s, k[3] / s };
 		hm_inverse_camera_matrix(p.invK[l].m, ks);
 	}
-	p.first[c->levels] = first;
+	p.first[fused] = first;
 	// right behind a preprocessing that went to the side stream: follow it there (same window, same readers)
 	const bool on_side = c->side_pending && !(c->timing & 3u);
-	k_pyramid<<<(first + 255) / 256, 256, 0, on_side ? c->side : c->stream>>>(p);
+	cudaStream_t st = on_side ? c->side : c->stream;
+	k_pyramid<<<(first + 255) / 256, 256, 0, st>>>(p);
 	LAUNCHED(c);
+	for (int l = 3; l < c->levels; ++l) {
+		const float s = (float) (1 << l);
+		const float ks[4] = { k[0] / s, k[1] / s, k[2] / s, k[3] / s };
+		Mat4 invK;
+		hm_inverse_camera_matrix(invK.m, ks);
+		const uint32_t n = c->lw[l] * c->lh[l];
+		k_pyramid_level<<<(n + 255) / 256, 256, 0, st>>>(c->d_scaled[l - 1], c->lw[l - 1], c->d_scaled[l], c->d_inV[l], c->d_inN[l], c->lw[l], c->lh[l], invK, c_e_delta * 3);
+		c->st.kernel_launches++;
+	}
 	CK(cudaGetLastError());
 	if (on_side) return join_side(c);
 	return 0;
@@ -688,12 +723,63 @@ int kfb_k_track_reduce(kfb_ctx* c, int level, const float T[16], const float V[1
 	return 0;
 }
 
+// the whole ICP schedule of one frame as ONE persistent cooperative kernel (k_icp); `tail` (optional) makes its last CTA
+// also evaluate checkPose and the matrices integrate / raycast need, into c->d_frame.  Returns the sequence number to wait for.
+static int launch_icp(kfb_ctx* c, float icp_threshold, const float* projectReference, const IcpTail* tail, uint32_t* seq_out) {
+	IcpParams p;
+	memset(&p, 0, sizeof p);
+	for (int l = 0; l < c->levels; ++l) {
+		p.inV[l] = c->d_inV[l]; p.inN[l] = c->d_inN[l]; p.w[l] = c->lw[l]; p.h[l] = c->lh[l];
+		p.iterations[l] = c->cfg.iterations[l];
+	}
+	p.levels = c->levels;
+	p.refV = c->d_vertex; p.refN = c->d_normal; p.rw = c->cw; p.rh = c->ch;
+	p.pose0 = toMat(c->pose); p.view = toMat(projectReference);
+	p.dist_threshold = c_dist_threshold; p.normal_threshold = c_normal_threshold; p.icp_threshold = icp_threshold;
+	p.partials = c->d_partials; p.bar = c->d_bar; p.pose_dev = c->d_pose; p.out32 = c->d_out32; p.prof = c->d_icp_prof;
+	p.out_host = c->h_out32_dev;
+	p.seq = ++c->seq;
+	p.status = (c->cfg.flags & KFB_FLAG_TRACK_STATUS) ? c->d_status : nullptr;
+	if (tail) p.tail = *tail;
+	c->h_out32[33] = 0.f;
+	void* args[] = { &p };
+	CK(cudaLaunchCooperativeKernel((const void*) k_icp, dim3(c->icp_grid), dim3(ICP_THREADS), args, ICP_SMEM_BYTES, c->stream));
+	LAUNCHED(c);
+	*seq_out = p.seq;
+	return 0;
+}
+// wait for that kernel's results (mapped host memory) and take them over: sums, pose, iteration count
+static int collect_icp(kfb_ctx* c, uint32_t seq, uint64_t* iters) {
+	int rc = wait_seq(c, seq);
+	if (rc) return rc;
+	if (*(volatile uint32_t*) (c->h_out32 + 33) != 0) {
+		cudaStreamSynchronize(c->stream);
+		cudaMemsetAsync(c->d_bar, 0, 4 * sizeof(unsigned int), c->stream);
+		return set_err(KFB_E_CUDA, "ICP kernel: grid barrier timed out");
+	}
+	memcpy(c->reduction, c->h_out32, 32 * sizeof(float));
+	memcpy(c->pose, c->h_out32 + 48, 16 * sizeof(float));
+	*iters = *(volatile uint32_t*) (c->h_out32 + 64);
+	c->st.d2h_bytes += (32 + 16 + 1) * sizeof(float);
+	return 0;
+}
+static int icp_total_iterations(const kfb_ctx* c) {
+	int total = 0;
+	for (int level = 0; level < c->levels; ++level) total += c->cfg.iterations[level] > 0 ? c->cfg.iterations[level] : 0;
+	return total;
+}
+
 int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracking_rate, uint32_t frame, int* tracked) {
 	if (!c || !k) return set_err(KFB_E_ARG, "null argument");
 	CK(cudaSetDevice(c->device));
 	if (tracked) *tracked = 0;
 	if (tracking_rate == 0) return set_err(KFB_E_ARG, "tracking_rate must be > 0");
-	if (frame % tracking_rate != 0) return 0;                       // cpp/kernels.cpp:927
+	if (frame % tracking_rate != 0) {                               // cpp/kernels.cpp:927
+		// preprocessing() is synchronous with respect to the caller's buffer in the reference: the asynchronous copy of this
+		// frame must have left it before the documented "reusable after the next kfb_track" holds
+		if (c->ev_h2d_pending) { CK(cudaEventSynchronize(c->ev_h2d)); c->ev_h2d_pending = false; }
+		return 0;
+	}
 	timer_begin(c, c->t_track, 2u);
 	int rc = launch_pyramid(c, k);                                  // :931-945
 	if (rc) return rc;
@@ -712,43 +798,14 @@ int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracki
 				if (hm_update_pose(c->pose, c->reduction, icp_threshold)) break;
 			}
 		}
-	} else {
+	} else if (icp_total_iterations(c) > 0) {
 		// device-resident loop: ONE persistent cooperative kernel runs the whole schedule (solve, pose
 		// update and the per-level `break` in its last-arriving CTA); ONE host wait per frame
-		int total = 0;
-		for (int level = 0; level < c->levels; ++level) total += c->cfg.iterations[level] > 0 ? c->cfg.iterations[level] : 0;
-		if (total > 0) {
-			IcpParams p;
-			memset(&p, 0, sizeof p);
-			for (int l = 0; l < c->levels; ++l) {
-				p.inV[l] = c->d_inV[l]; p.inN[l] = c->d_inN[l]; p.w[l] = c->lw[l]; p.h[l] = c->lh[l];
-				p.iterations[l] = c->cfg.iterations[l];
-			}
-			p.levels = c->levels;
-			p.refV = c->d_vertex; p.refN = c->d_normal; p.rw = c->cw; p.rh = c->ch;
-			p.pose0 = toMat(c->pose); p.view = toMat(projectReference);
-			p.dist_threshold = c_dist_threshold; p.normal_threshold = c_normal_threshold; p.icp_threshold = icp_threshold;
-			p.partials = c->d_partials; p.bar = c->d_bar; p.pose_dev = c->d_pose; p.out32 = c->d_out32; p.prof = c->d_icp_prof;
-			p.out_host = c->h_out32_dev;
-			p.seq = ++c->seq;
-			p.status = (c->cfg.flags & KFB_FLAG_TRACK_STATUS) ? c->d_status : nullptr;
-			c->h_out32[33] = 0.f;
-			void* args[] = { &p };
-			CK(cudaLaunchCooperativeKernel((const void*) k_icp, dim3(c->icp_grid), dim3(ICP_THREADS), args, ICP_SMEM_BYTES, c->stream));
-			LAUNCHED(c);
-			rc = wait_seq(c, p.seq);
-			if (rc) return rc;
-			if (*(volatile uint32_t*) (c->h_out32 + 33) != 0) {
-				cudaStreamSynchronize(c->stream);
-				cudaMemsetAsync(c->d_bar, 0, 4 * sizeof(unsigned int), c->stream);
-				return set_err(KFB_E_CUDA, "ICP kernel: grid barrier timed out");
-			}
-			memcpy(c->reduction, c->h_out32, 32 * sizeof(float));
-			memcpy(c->pose, c->h_out32 + 48, 16 * sizeof(float));
-			iters = *(volatile uint32_t*) (c->h_out32 + 64);
-			c->st.d2h_bytes += (32 + 16 + 1) * sizeof(float);
-		}
+		uint32_t seq;
+		if ((rc = launch_icp(c, icp_threshold, projectReference, nullptr, &seq))) return rc;
+		if ((rc = collect_icp(c, seq, &iters))) return rc;
 	}
+	c->ev_h2d_pending = false;   // the stream has passed the copy
 	timer_end(c, c->t_track, 2u);
 	c->st.icp_iterations_last = iters;
 	c->st.icp_iterations_total += iters;
@@ -758,7 +815,7 @@ int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracki
 }
 
 // --------------------------------------------------------------------------- integration
-static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, float mu, float maxweight) {
+static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, float mu, float maxweight, const DevFrame* dev = nullptr) {
 	// everything the next frame's preprocessing rewrites has been read by now, except the raw depth and its maximum,
 	// which are double- / triple-buffered: its window (kfb_ctx::side) opens here
 	if (c->overlap_enabled) CK(cudaEventRecord(c->ev_window, c->stream));
@@ -769,9 +826,13 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	p.z_begin = c->z0; p.z_end = c->z1;
 	p.depth = c->d_floatDepth; p.dw = c->cw; p.dh = c->ch;
 	p.invTrack = toMat(invTrack); p.K = toMat(K);
+	p.dev = dev;               // non-null: invTrack and the integrate gate come from the ICP kernel's tail
 	p.mu = mu; p.maxweight = maxweight;
 	p.cull = (c->cfg.flags & KFB_FLAG_INTEGRATE_NO_CULL) ? 0 : 1;
 	p.brick = c->brick;
+	p.brick.n_peer = 0;
+	if (c->peer_mode && c->brick.flag)
+		for (int r = 0; r < c->world; ++r) if (r != c->rank && c->peer_bricks[r]) p.brick.peer[p.brick.n_peer++] = c->peer_bricks[r];
 	if (maxweight > 200.f && c->brick.flag) {
 		// the flagging rule in k_integrate_run assumes w + 1 <= 201; beyond that stop using (and maintaining) the flags
 		c->view_all.brick = nullptr; p.brick.flag = nullptr; c->brick_off = true;
@@ -845,7 +906,7 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	}
 	CK(cudaGetLastError());
 	c->integrate_count++;
-	c->st.frames_integrated++;
+	if (!dev) c->st.frames_integrated++;   // device-gated launches are counted when the host learns the gate
 	c->overlap_ok = c->overlap_enabled;   // until anything but the raycast is enqueued
 	return 0;
 }
@@ -874,12 +935,19 @@ int kfb_integrate(kfb_ctx* c, const float k[4], uint32_t integration_rate, float
 		doIntegrate = 1;
 	} else doIntegrate = 0;
 	if (integrated) *integrated = doIntegrate;
+	// z-slab group: every slab (and every flag stored into a peer) is complete before anybody raycasts through it.  All
+	// ranks hold the same pose and flags, so all of them come through here, integrated or not.
+	if (c->peer_mode) return kfb_peer_barrier(c);
 	return 0;
 }
 
 // ---------------------------------------------------------------------------- raycasting
-static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP, float step, float largestep) {
+static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP, float step, float largestep, const float* view_dev = nullptr) {
 	RaycastParams p;
+	p.view_dev = view_dev;
+	p.n_peer = 0;
+	if (c->peer_mode)
+		for (int r = 0; r < c->world; ++r) if (r != c->rank) { p.peer_vertex[p.n_peer] = c->peer_vertex[r]; p.peer_normal[p.n_peer] = c->peer_normal[r]; ++p.n_peer; }
 	p.vol = c->view_all;
 	p.tile_cost = c->d_tile_cost;
 	p.vertex = c->d_vertex; p.normal = c->d_normal;
@@ -916,19 +984,90 @@ int kfb_raycast(kfb_ctx* c, const float k[4], float mu, uint32_t frame) {
 		hm_matmul4(view, c->raycastPose, invK);
 		timer_begin(c, c->t_ray, 8u);
 		int rc = launch_raycast(c, view, c_nearPlane, c_farPlane, c->step, 0.75f * mu);   // :979-981
+		// z-slab group: all bands have landed in this rank's maps before the next ICP reads them, and nobody integrates the
+		// next frame into a slab a peer's rays are still reading
+		if (!rc && c->peer_mode) rc = kfb_peer_barrier(c);
 		timer_end(c, c->t_ray, 8u);
 		return rc;
 	}
 	return 0;
 }
 
+// track -> integrate -> raycast of Kfusion::computeFrame, after the preprocessing of either entry point
+static int compute_frame_rest(kfb_ctx* c, const float k[4], uint32_t integration_rate, uint32_t tracking_rate, float icp_threshold, float mu,
+		uint32_t frame, int* tracked, int* integrated) {
+	int rc;
+	// Kfusion::computeFrame (cpp/kernels.cpp:1048-1055) is the one entry point that knows the whole frame up front, so
+	// the whole frame is ENQUEUED before the host has seen the pose: the ICP kernel's last CTA evaluates checkPose,
+	// inverse(pose) and raycastPose * invK on the device (same routines as the host path: bit-identical) and the integrate
+	// / raycast kernels read them from device memory; the host only waits for the ICP result (tracked, integrated, pose)
+	// while integrate and raycast are already running.  Frames without tracking, the host-solve A/B mode, stage timers and
+	// z-slab contexts (collectives of the caller between the stages) take the staged path.
+	const bool whole = (frame % tracking_rate == 0) && !(c->cfg.flags & KFB_FLAG_ICP_HOST_SOLVE) && icp_total_iterations(c) > 0
+			&& c->world == 1 && (c->timing & 3u) == 0 && !c->no_async;   // integrate / raycast timers are in-stream events: no sync
+	if (!whole) {
+		if ((rc = kfb_track(c, k, icp_threshold, tracking_rate, frame, tracked))) return rc;
+		if ((rc = kfb_integrate(c, k, integration_rate, mu, frame, integrated))) return rc;
+		return kfb_raycast(c, k, mu, frame);
+	}
+	CK(cudaSetDevice(c->device));
+	if ((rc = launch_pyramid(c, k))) return rc;                     // :931-945
+	memcpy(c->oldPose, c->pose, sizeof c->pose);                    // :947
+	float K[16], invK[16], invRP[16], projectReference[16];
+	hm_camera_matrix(K, k);
+	hm_inverse_camera_matrix(invK, k);
+	hm_inverse4(invRP, c->raycastPose);
+	hm_matmul4(projectReference, K, invRP);                         // :948
+	IcpTail tail;
+	tail.out = c->d_frame;
+	tail.K = toMat(K); tail.invK = toMat(invK);
+	tail.track_threshold = c_track_threshold;
+	tail.force_integrate = frame <= 3;                              // :994
+	tail.rate_ok = (frame % integration_rate) == 0;
+	uint32_t seq;
+	if ((rc = launch_icp(c, icp_threshold, projectReference, &tail, &seq))) return rc;
+	// integrate: launched unconditionally, gated on the device (DevFrame::do_integrate)
+	timer_begin(c, c->t_int, 4u);
+	rc = launch_integrate(c, c->pose /* unused */, K, mu, c_maxweight, c->d_frame);
+	timer_end(c, c->t_int, 4u);
+	if (rc) return rc;
+	if (frame > 2) {                                                // :977-981
+		timer_begin(c, c->t_ray, 8u);
+		rc = launch_raycast(c, c->pose /* unused */, c_nearPlane, c_farPlane, c->step, 0.75f * mu, c->d_frame->view);
+		timer_end(c, c->t_ray, 8u);
+		if (rc) return rc;
+	}
+	uint64_t iters = 0;
+	if ((rc = collect_icp(c, seq, &iters))) return rc;              // pose is already the one checkPose left (oldPose if lost)
+	c->ev_h2d_pending = false;
+	c->st.icp_iterations_last = iters;
+	c->st.icp_iterations_total += iters;
+	const int ok = (int) *(volatile uint32_t*) (c->h_out32 + 65), did = (int) *(volatile uint32_t*) (c->h_out32 + 66);
+	c->st.d2h_bytes += 2 * sizeof(uint32_t);
+	if (did) c->st.frames_integrated++;
+	if (frame > 2) memcpy(c->raycastPose, c->pose, sizeof c->pose); // :978
+	if (tracked) *tracked = ok;
+	if (integrated) *integrated = did;
+	return 0;
+}
+
 int kfb_compute_frame(kfb_ctx* c, const uint16_t* depth, uint32_t iw, uint32_t ih, const float k[4], uint32_t integration_rate,
 		uint32_t tracking_rate, float icp_threshold, float mu, uint32_t frame, int* tracked, int* integrated) {
 	int rc;
+	if (!c || !k) return set_err(KFB_E_ARG, "null argument");
+	if (tracking_rate == 0) return set_err(KFB_E_ARG, "tracking_rate must be > 0");
+	if (integration_rate == 0) return set_err(KFB_E_ARG, "integration_rate must be > 0");
 	if ((rc = kfb_preprocess(c, depth, iw, ih))) return rc;
-	if ((rc = kfb_track(c, k, icp_threshold, tracking_rate, frame, tracked))) return rc;
-	if ((rc = kfb_integrate(c, k, integration_rate, mu, frame, integrated))) return rc;
-	return kfb_raycast(c, k, mu, frame);
+	return compute_frame_rest(c, k, integration_rate, tracking_rate, icp_threshold, mu, frame, tracked, integrated);
+}
+int kfb_compute_frame_device(kfb_ctx* c, const uint16_t* d_depth, uint32_t iw, uint32_t ih, const float k[4], uint32_t integration_rate,
+		uint32_t tracking_rate, float icp_threshold, float mu, uint32_t frame, int* tracked, int* integrated) {
+	int rc;
+	if (!c || !k) return set_err(KFB_E_ARG, "null argument");
+	if (tracking_rate == 0) return set_err(KFB_E_ARG, "tracking_rate must be > 0");
+	if (integration_rate == 0) return set_err(KFB_E_ARG, "integration_rate must be > 0");
+	if ((rc = kfb_preprocess_device(c, d_depth, iw, ih))) return rc;
+	return compute_frame_rest(c, k, integration_rate, tracking_rate, icp_threshold, mu, frame, tracked, integrated);
 }
 
 // ------------------------------------------------------------------------------- renders
@@ -1155,6 +1294,73 @@ int kfb_slab_import(kfb_ctx* c, int rank, int world, const uint8_t* handles64, c
 	}
 	c->view_all.slab_z[world] = c->cfg.volume_res[2];
 	if (z_begin[rank] != c->z0) return set_err(KFB_E_ARG, "z_begin[%d]=%u does not match this context's slab start %u", rank, z_begin[rank], c->z0);
+	return 0;
+}
+int kfb_ipc_export(kfb_ctx* c, kfb_ipc_handles* out) {
+	if (!c || !out) return set_err(KFB_E_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	memset(out, 0, sizeof *out);
+	cudaIpcMemHandle_t h;
+	static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+	CK(cudaIpcGetMemHandle(&h, c->d_vol)); memcpy(out->volume, &h, 64);
+	CK(cudaIpcGetMemHandle(&h, c->d_vertex)); memcpy(out->vertex, &h, 64);
+	CK(cudaIpcGetMemHandle(&h, c->d_normal)); memcpy(out->normal, &h, 64);
+	CK(cudaIpcGetMemHandle(&h, c->d_sync)); memcpy(out->sync, &h, 64);
+	if (c->brick.flag) { CK(cudaIpcGetMemHandle(&h, c->brick.flag)); memcpy(out->bricks, &h, 64); out->has_bricks = 1; }
+	out->slab_z0 = c->z0; out->slab_z1 = c->z1;
+	return 0;
+}
+int kfb_ipc_import(kfb_ctx* c, int rank, int world, const kfb_ipc_handles* all) {
+	if (!c || !all) return set_err(KFB_E_ARG, "null argument");
+	if (world < 1 || world > KFB_MAX_SLABS || rank < 0 || rank >= world) return set_err(KFB_E_ARG, "bad rank/world %d/%d", rank, world);
+	if (all[rank].slab_z0 != c->z0 || all[rank].slab_z1 != c->z1) return set_err(KFB_E_ARG, "handles[%d] do not describe this context's slab", rank);
+	for (int r = 0; r + 1 < world; ++r)
+		if (all[r].slab_z1 != all[r + 1].slab_z0) return set_err(KFB_E_ARG, "slabs %d and %d are not contiguous in z", r, r + 1);
+	if (all[0].slab_z0 != 0 || all[world - 1].slab_z1 != c->cfg.volume_res[2]) return set_err(KFB_E_ARG, "the slabs do not cover the volume");
+	CK(cudaSetDevice(c->device));
+	c->rank = rank; c->world = world;
+	c->view_all.n_slabs = world;
+	if (world > 1) { c->overlap_enabled = false; c->overlap_ok = false; c->side_pending = false; }
+	bool all_bricks = c->brick.flag != nullptr;
+	for (int r = 0; r < world; ++r) all_bricks = all_bricks && all[r].has_bricks;
+	if (!all_bricks) c->view_all.brick = nullptr;       // without every rank's flags the raycaster must not skip
+	auto open = [&](const uint8_t* h64, void** out) -> int {
+		cudaIpcMemHandle_t h;
+		memcpy(&h, h64, 64);
+		CK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+		return 0;
+	};
+	for (int r = 0; r < world; ++r) {
+		c->view_all.slab_z[r] = all[r].slab_z0;
+		if (r == rank) {
+			c->view_all.slab_ptr[r] = c->d_vol;
+			c->sync_all.p[r] = c->d_sync;
+			continue;
+		}
+		int rc;
+		void* p = nullptr;
+		if ((rc = open(all[r].volume, &p))) return rc;
+		c->peer_ptrs[r] = p; c->view_all.slab_ptr[r] = (const short2*) p;
+		if ((rc = open(all[r].vertex, &c->peer_open[r][0]))) return rc;
+		if ((rc = open(all[r].normal, &c->peer_open[r][1]))) return rc;
+		if (all_bricks && (rc = open(all[r].bricks, &c->peer_open[r][2]))) return rc;
+		if ((rc = open(all[r].sync, &c->peer_open[r][3]))) return rc;
+		c->peer_vertex[r] = (float*) c->peer_open[r][0]; c->peer_normal[r] = (float*) c->peer_open[r][1];
+		c->peer_bricks[r] = (unsigned char*) c->peer_open[r][2];
+		c->sync_all.p[r] = (PeerSync*) c->peer_open[r][3];
+	}
+	c->view_all.slab_z[world] = c->cfg.volume_res[2];
+	c->peer_mode = world > 1;
+	c->barrier_count = 0;
+	return 0;
+}
+int kfb_peer_barrier(kfb_ctx* c) {
+	if (!c) return set_err(KFB_E_ARG, "null ctx");
+	if (!c->peer_mode) return 0;
+	CK(cudaSetDevice(c->device));
+	k_peer_barrier<<<1, KFB_MAX_SLABS, 0, c->stream>>>(c->sync_all, c->rank, c->world, ++c->barrier_count, (volatile unsigned int*) (c->h_out32_dev + 34));
+	LAUNCHED(c);
+	CK(cudaGetLastError());
 	return 0;
 }
 int kfb_set_pixel_rows(kfb_ctx* c, uint32_t row0, uint32_t row1) {

@@ -163,7 +163,8 @@ struct Integrate2Params {
 	int maxw_i;               // floor(maxweight) when the integer weight update is exact (1 <= maxweight <= 32767), else -1
 	int vec_ok;               // sx % 8 == 0: 128-bit voxel accesses are aligned and every x-brick is complete
 	int std_k;                // K's third row is (0, 0, 1, 0): cameraX.z == pos.z bit for bit
-	// classification geometry, evaluated once per launch on the host (approximate values: the margins cover them)
+	// classification geometry (approximate values: the margins cover them); ca / tz follow invTrack: from the host, or from
+	// the ICP kernel's tail (b.dev)
 	float vsz[3];             // voxel size (m)
 	float ca[9];              // K.rot * invTrack.rot, row-major: camera-space step per metre along the volume's x, y, z
 	float tz[3];              // third row of invTrack.rot: pos.z per metre along x, y, z
@@ -176,28 +177,39 @@ struct Integrate2Params {
 	unsigned int* ctr_next;   // the other slot's four counters, zeroed by the plan pass for the next launch
 };
 
+// invTrack and what is derived from it, in shared memory: by value from the host (staged API) or from the ICP kernel's tail
+struct IntGeom { Mat4 invTrack; float ca[9], tz[3]; };
+// returns false when the device-side gate says "no integrate this frame" (cpp/kernels.cpp:994)
+__device__ __forceinline__ bool int_geom_load(IntGeom& g, const Integrate2Params& q, uint32_t tid) {
+	const DevFrame* d = q.b.dev;
+	if (tid < 16) g.invTrack.m[tid] = d ? __ldcg(d->invTrack + tid) : q.b.invTrack.m[tid];
+	else if (tid < 25) g.ca[tid - 16] = d ? __ldcg(d->ca + (tid - 16)) : q.ca[tid - 16];
+	else if (tid < 28) g.tz[tid - 25] = d ? __ldcg(d->tz + (tid - 25)) : q.tz[tid - 25];
+	__syncthreads();
+	return !(d && __ldcg(&d->do_integrate) == 0);
+}
+
 // Class of the box of voxels [x0, x1] x [y0, y1] x [z0, z1] (inclusive), from linear bounds over the box of their centres
 // and its 8 projected corners (see the file header).  FREE is only claimed where the caller may use it (`allow_free`).
-__device__ __noinline__ int classify_box(const Integrate2Params& q, uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1, uint32_t z0, uint32_t z1,
-		float dmax_all, bool allow_free) {
+__device__ __noinline__ int classify_box(const Integrate2Params& q, const IntGeom& g, uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
+		uint32_t z0, uint32_t z1, float dmax_all, bool allow_free) {
 	const IntegrateParams& p = q.b;
 	const float vx = q.vsz[0], vy = q.vsz[1], vz = q.vsz[2];
 	// box of the voxel CENTRES (Volume::pos, commons.h:186-189): centre and half extents in metres
 	const float3 ctr = f3(((float) (x0 + x1) * 0.5f + 0.5f) * vx, ((float) (y0 + y1) * 0.5f + 0.5f) * vy, ((float) (z0 + z1) * 0.5f + 0.5f) * vz);
 	const float hx = (float) (x1 - x0) * 0.5f * vx, hy = (float) (y1 - y0) * 0.5f * vy, hz = (float) (z1 - z0) * 0.5f * vz;
-	const Mat4& T = p.invTrack;
-	const float3 pc = mat_point(T, ctr);
+	const float3 pc = mat_point(g.invTrack, ctr);
 	const float3 cc = mat_point(p.K, pc);
 	// camera-space offsets of the three box axes: columns of (K.rot * T.rot) scaled by the half extents
-	const float3 a0 = f3(q.ca[0], q.ca[3], q.ca[6]) * hx, a1 = f3(q.ca[1], q.ca[4], q.ca[7]) * hy, a2 = f3(q.ca[2], q.ca[5], q.ca[8]) * hz;
-	const float hpz = fabsf(q.tz[0]) * hx + fabsf(q.tz[1]) * hy + fabsf(q.tz[2]) * hz;   // half extent of pos.z
+	const float3 a0 = f3(g.ca[0], g.ca[3], g.ca[6]) * hx, a1 = f3(g.ca[1], g.ca[4], g.ca[7]) * hy, a2 = f3(g.ca[2], g.ca[5], g.ca[8]) * hz;
+	const float hpz = fabsf(g.tz[0]) * hx + fabsf(g.tz[1]) * hy + fabsf(g.tz[2]) * hz;   // half extent of pos.z
 	const float hcx = fabsf(a0.x) + fabsf(a1.x) + fabsf(a2.x), hcy = fabsf(a0.y) + fabsf(a1.y) + fabsf(a2.y), hcz = fabsf(a0.z) + fabsf(a1.z) + fabsf(a2.z);
 	// bound on the drift of the reference's accumulated values from the exact line: (N + 64) * 2^-22 times the largest
 	// magnitude along the column (k_integrate_plan uses the same bound); the column spans dz in z
 	const float eps = ((float) p.sz + 64.f) * 2.3841858e-7f;
-	const float3 kz = f3(q.ca[2], q.ca[5], q.ca[8]) * p.dz;   // change of cam over the whole column
+	const float3 kz = f3(g.ca[2], g.ca[5], g.ca[8]) * p.dz;   // change of cam over the whole column
 	const float cxm = fabsf(cc.x) + hcx, cym = fabsf(cc.y) + hcy, czm = fabsf(cc.z) + hcz;   // magnitudes inside the box
-	const float e_pz = eps * (fabsf(pc.z) + hpz + fabsf(q.tz[2]) * p.dz);
+	const float e_pz = eps * (fabsf(pc.z) + hpz + fabsf(g.tz[2]) * p.dz);
 	const float e_cx = eps * (cxm + fabsf(kz.x)), e_cy = eps * (cym + fabsf(kz.y)), e_cz = eps * (czm + fabsf(kz.z));
 	const float pz_min = pc.z - hpz - e_pz, pz_max = pc.z + hpz + e_pz;
 	const float cz_min = cc.z - hcz - e_cz, cz_max = cc.z + hcz + e_cz;
@@ -284,10 +296,12 @@ __device__ __forceinline__ unsigned int item_len(unsigned int m, uint32_t lane, 
 
 __global__ void __launch_bounds__(256, 3) k_integrate_plan2(const __grid_constant__ Integrate2Params q) {
 	__shared__ unsigned int s_mm[8][PLAN_GROUPS], s_ms[8][PLAN_GROUPS];
+	__shared__ IntGeom geom;
 	const IntegrateParams& p = q.b;
 	const uint32_t lane = threadIdx.x;
 	const uint32_t bx = blockIdx.x, by = blockIdx.y * blockDim.y + threadIdx.y;   // warp-uniform
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 4 && threadIdx.y == 0) q.ctr_next[threadIdx.x] = 0u;   // re-arm the other slot
+	if (!int_geom_load(geom, q, threadIdx.y * 32 + threadIdx.x)) return;   // gate closed: no items, the run pass finds none
 	if (by >= q.bny) return;
 	const uint32_t bz0 = p.z_begin >> 3, bz1 = (p.z_end + 7) >> 3;
 	const bool fast = p.cull && p.mu > 0.f && p.dw <= 2040 && p.dh <= 2040;
@@ -296,7 +310,7 @@ __global__ void __launch_bounds__(256, 3) k_integrate_plan2(const __grid_constan
 	const unsigned int lt = (1u << lane) - 1u;
 	const uint32_t x0 = bx * 8, x1 = min(x0 + 7, p.sx - 1), y0 = by * 8, y1 = min(y0 + 7, p.sy - 1);
 	// the whole column first (most columns lie outside the view frustum: one test instead of one per brick)
-	if (fast && classify_box(q, x0, x1, y0, y1, p.z_begin, p.z_end - 1, dmax_all, false) == CLS_SKIP) {
+	if (fast && classify_box(q, geom, x0, x1, y0, y1, p.z_begin, p.z_end - 1, dmax_all, false) == CLS_SKIP) {
 		for (uint32_t bz = bz0 + lane; bz < bz1; bz += 32) q.cls[((size_t) (bz - bz0) * q.bny + by) * q.bnx + bx] = CLS_SKIP;
 		return;
 	}
@@ -312,7 +326,7 @@ __global__ void __launch_bounds__(256, 3) k_integrate_plan2(const __grid_constan
 			const uint32_t bz = pass0 + 32 * g + lane;
 			int c = CLS_SKIP;
 			if (bz < bz1) {
-				c = fast ? classify_box(q, x0, x1, y0, y1, bz * 8, min(bz * 8 + 7, p.sz - 1), dmax_all, q.vec_ok != 0) : CLS_MIXED_EDGE;
+				c = fast ? classify_box(q, geom, x0, x1, y0, y1, bz * 8, min(bz * 8 + 7, p.sz - 1), dmax_all, q.vec_ok != 0) : CLS_MIXED_EDGE;
 				q.cls[((size_t) (bz - bz0) * q.bny + by) * q.bnx + bx] = (unsigned char) c;
 			}
 			const unsigned int m_mixed = __ballot_sync(0xffffffffu, c >= CLS_MIXED_IN), m_starts = item_starts(m_mixed, lane, INT_MIXED_CAP);
@@ -356,7 +370,7 @@ __global__ void __launch_bounds__(256, 3) k_integrate_plan2(const __grid_constan
 					const uint32_t tbz = pass0 + 32 * g + __fns(m_mixed, 0, (int) (t >> 2) + 1), hs = t & 3u;
 					const uint32_t cy0 = y0 + 4 * (hs >> 1), cz0 = tbz * 8 + 4 * (hs & 1);
 					c = CLS_SKIP;
-					if (cy0 < p.sy && cz0 < p.z_end) c = classify_box(q, x0, x1, cy0, min(cy0 + 3, p.sy - 1), cz0, min(cz0 + 3, p.sz - 1), dmax_all, true);
+					if (cy0 < p.sy && cz0 < p.z_end) c = classify_box(q, geom, x0, x1, cy0, min(cy0 + 3, p.sy - 1), cz0, min(cz0 + 3, p.sz - 1), dmax_all, true);
 				}
 #pragma unroll
 				for (unsigned int hs = 0; hs < 4; ++hs) {
@@ -415,11 +429,11 @@ __device__ __forceinline__ size_t ready_index(const Integrate2Params& q, uint32_
 }
 
 // REPLAY job: the lanes are the 8 x 4 voxel columns of one column half; one sweep from z = 0 past every item start
-__device__ __forceinline__ void integrate_replay_job(const Integrate2Params& q, uint4 job, uint32_t lane) {
+__device__ __forceinline__ void integrate_replay_job(const Integrate2Params& q, const IntGeom& geom, uint4 job, uint32_t lane) {
 	const IntegrateParams& p = q.b;
 	const uint32_t bx = job.x & 0xfffu, by = (job.x >> 12) & 0xfffu, half = (job.x >> 24) & 1u;
 	const uint32_t x = bx * 8 + (lane & 7), y = by * 8 + half * 4 + (lane >> 3);
-	const IntColumn c = int_column(p, x, y);
+	const IntColumn c = int_column(p, geom.invTrack, x, y);
 	// running values, packed in pairs: (pos.x, pos.y) (pos.z, cam.x) (cam.y, cam.z)
 	F2 A = f2_make(c.pos0.x, c.pos0.y), B = f2_make(c.pos0.z, c.cam0.x), C = f2_make(c.cam0.y, c.cam0.z);
 	const F2 dA = f2_make(c.delta.x, c.delta.y), dB = f2_make(c.delta.z, c.cameraDelta.x), dC = f2_make(c.cameraDelta.y, c.cameraDelta.z);
@@ -441,9 +455,10 @@ __device__ __forceinline__ void integrate_replay_job(const Integrate2Params& q, 
 
 __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integrate2Params q) {
 	__shared__ float rcp[128];
+	__shared__ IntGeom geom;
 	const IntegrateParams& p = q.b;
 	if (threadIdx.x < 128) rcp[threadIdx.x] = 1.0f / (float) threadIdx.x;   // [0] = inf, never used
-	__syncthreads();
+	if (!int_geom_load(geom, q, threadIdx.x)) return;
 	const uint32_t lane = threadIdx.x & 31;
 	const float dwm1 = (float) (p.dw - 1), dhm1 = (float) (p.dh - 1);
 	const bool fast = p.cull && p.mu > 0.f && p.dw <= 2040 && p.dh <= 2040;
@@ -467,7 +482,7 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 		if (it >= n_items) break;
 		if (lane == 0) nxt = atomicAdd(q.ctr + 2, 1u);
 		if (it < n_replay) {
-			integrate_replay_job(q, __ldcg(q.q_replay + it), lane);
+			integrate_replay_job(q, geom, __ldcg(q.q_replay + it), lane);
 			continue;
 		}
 		it -= n_replay;
@@ -537,7 +552,7 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 		// reference's additions from z = 0 here
 		F2 A, B, C, dA, dB, dC;
 		{
-			const float3 delta = mat_rotate(p.invTrack, f3(0, 0, p.dz / (float) p.sz)), cameraDelta = mat_rotate(p.K, delta);
+			const float3 delta = mat_rotate(geom.invTrack, f3(0, 0, p.dz / (float) p.sz)), cameraDelta = mat_rotate(p.K, delta);
 			dA = f2_make(delta.x, delta.y); dB = f2_make(delta.z, cameraDelta.x); dC = f2_make(cameraDelta.y, cameraDelta.z);
 		}
 		bool have = false;
@@ -555,7 +570,7 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 			const unsigned long long* o = q.ckpt + (size_t) idx * 96 + lane;
 			A.v = __ldcg(o); B.v = __ldcg(o + 32); C.v = __ldcg(o + 64);
 		} else {
-			const IntColumn c = int_column(p, x, y);
+			const IntColumn c = int_column(p, geom.invTrack, x, y);
 			A = f2_make(c.pos0.x, c.pos0.y); B = f2_make(c.pos0.z, c.cam0.x); C = f2_make(c.cam0.y, c.cam0.z);
 #pragma unroll 8
 			for (int z = 0; z < za; ++z) { A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC); }
@@ -629,7 +644,7 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 						if (ddy) m &= (half == 0) ? 0x000000ffu : 0u;  // lanes with y % 8 == 0
 						const uint32_t bz = (uint32_t) z >> BRICK_SHIFT;
 						if (m && bx >= ddx && by >= ddy && bz >= ddz)
-							p.brick.flag[((size_t) (bz - ddz) * p.brick.bny + (by - ddy)) * p.brick.bnx + (bx - ddx)] = 1;
+							brick_set(p.brick, ((size_t) (bz - ddz) * p.brick.bny + (by - ddy)) * p.brick.bnx + (bx - ddx));
 					}
 				}
 			}

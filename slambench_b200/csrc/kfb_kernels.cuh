@@ -155,6 +155,30 @@ __global__ void __launch_bounds__(256) k_pyramid(PyrParams p) {
 	st3(p.normal[level], local, knormalize(kcross(dyv, dxv)));
 }
 
+// Levels beyond the third (the reference accepts any `-y` list, default_parameters.h:394-396): one launch per level,
+// each from the STORED depth of the level above — same halfSample / depth2vertex / vertex2normal arithmetic.
+__global__ void __launch_bounds__(256) k_pyramid_level(const float* __restrict__ dprev, uint32_t pw, float* __restrict__ depth,
+		float* __restrict__ vertex, float* __restrict__ normal, uint32_t w, uint32_t h, Mat4 invK, float e_d) {
+	const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= w * h) return;
+	const int x = tid % w, y = tid / w;
+	auto lp = [&](int xx, int yy) { return __ldg(dprev + (size_t) xx + (size_t) yy * pw); };
+	auto dep = [&](int xx, int yy) { return half_sample(lp, xx, yy, e_d); };
+	auto vtx = [&](int xx, int yy) {
+		const float d = dep(xx, yy);
+		return d > 0 ? d * mat_rotate(invK, f3((float) xx, (float) yy, 1.f)) : f3(0, 0, 0);
+	};
+	depth[tid] = dep(x, y);
+	st3(vertex, tid, vtx(x, y));
+	const float3 left = vtx(kmaxi(x - 1, 0), y), right = vtx(kmini(x + 1, (int) w - 1), y);
+	const float3 up = vtx(x, kmaxi(y - 1, 0)), down = vtx(x, kmini(y + 1, (int) h - 1));
+	if (left.z == 0 || right.z == 0 || up.z == 0 || down.z == 0) {
+		normal[3 * (size_t) tid] = KFB_INVALID;
+		return;
+	}
+	st3(normal, tid, knormalize(kcross(down - up, right - left)));
+}
+
 // ------------------------------------------------------------------------------------------
 // trackKernel + reduceKernel FUSED (cpp/kernels.cpp:497-560, 251-495).
 // The reference writes a 32-byte TrackData per pixel to memory and re-reads it in a second
@@ -413,7 +437,25 @@ __global__ void __launch_bounds__(TR_THREADS) k_track_reduce(TrackParams p) {
 // trip and no skipped work between iterations; the host waits once per frame.
 // Launched with cudaLaunchCooperativeKernel (all CTAs co-resident: they wait on one another).
 // ------------------------------------------------------------------------------------------
-#define ICP_MAX_LEVELS 3
+// Frame state produced ON THE DEVICE by the ICP kernel's tail (checkPoseKernel cpp/kernels.cpp:777-792, inverse(pose)
+// commons.h:365-371, raycastPose * invK :979) and consumed by the integrate / raycast kernels of the same frame, so that
+// Kfusion::computeFrame can enqueue the whole frame before the host has seen the pose.
+struct DevFrame {
+	float pose[16];        // pose after checkPose (oldPose again when tracking failed)
+	float invTrack[16];    // inverse(pose): integrate
+	float view[16];        // pose * getInverseCameraMatrix(k): raycast
+	float ca[9], tz[3];    // integrate's classification geometry: K.rot * invTrack.rot; third row of invTrack.rot
+	int tracked, do_integrate;
+};
+struct IcpTail {
+	DevFrame* out;         // nullptr: no tail (the host evaluates checkPose / the matrices itself)
+	Mat4 K, invK;          // getCameraMatrix(k), getInverseCameraMatrix(k)
+	float track_threshold;
+	int force_integrate;   // frame <= 3                      (cpp/kernels.cpp:994)
+	int rate_ok;           // frame % integration_rate == 0
+};
+
+#define ICP_MAX_LEVELS 8
 struct IcpParams {
 	const float* inV[ICP_MAX_LEVELS]; const float* inN[ICP_MAX_LEVELS];
 	uint32_t w[ICP_MAX_LEVELS], h[ICP_MAX_LEVELS];
@@ -431,6 +473,7 @@ struct IcpParams {
 	float* out_host;                        // mapped: [0..31] sums, [32] seq, [33] error, [48..63] pose, [64] iterations
 	uint32_t seq;
 	int8_t* status;
+	IcpTail tail;
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -465,13 +508,39 @@ __device__ __forceinline__ unsigned long long gtime_ns() {
 	return t;
 }
 
+// one thread, after the last iteration: what Kfusion::tracking / integration / raycasting compute on the host between the
+// kernels (cpp/kernels.cpp:968, 991-996, 978-981), with the same __host__ __device__ routines the host path uses
+__device__ __noinline__ void icp_tail(const IcpParams& p) {
+	float pose[16], old[16], red[32];
+#pragma unroll
+	for (int i = 0; i < 16; ++i) { pose[i] = __ldcg(p.pose_dev + i); old[i] = p.pose0.m[i]; }
+#pragma unroll
+	for (int i = 0; i < 32; ++i) red[i] = __ldcg(p.out32 + i);
+	const int tracked = hm_check_pose(pose, old, red, p.rw, p.rh, p.tail.track_threshold);
+	DevFrame* f = p.tail.out;
+	float inv[16], view[16];
+	hm_inverse4(inv, pose);
+	hm_matmul4(view, pose, p.tail.invK.m);
+#pragma unroll
+	for (int i = 0; i < 16; ++i) { f->pose[i] = pose[i]; f->invTrack[i] = inv[i]; f->view[i] = view[i]; p.pose_dev[i] = pose[i]; }
+	for (int r = 0; r < 3; ++r)
+		for (int c = 0; c < 3; ++c)
+			f->ca[3 * r + c] = p.tail.K.m[4 * r + 0] * inv[c] + p.tail.K.m[4 * r + 1] * inv[4 + c] + p.tail.K.m[4 * r + 2] * inv[8 + c];
+	f->tz[0] = inv[8]; f->tz[1] = inv[9]; f->tz[2] = inv[10];
+	f->tracked = tracked;
+	f->do_integrate = (p.tail.force_integrate || (tracked && p.tail.rate_ok)) ? 1 : 0;
+	volatile unsigned int* h = reinterpret_cast<volatile unsigned int*>(p.out_host);
+	h[65] = (unsigned int) tracked;
+	h[66] = (unsigned int) f->do_integrate;
+}
+
 #ifndef ICP_THREADS
 #define ICP_THREADS 512   // one CTA per SM: half the partial rows for the last CTA to sum (measured 12.0 -> 11.3 us / iteration)
 #endif
 #define ICP_NW (ICP_THREADS / 32)          // warps per CTA
 #define ICP_VPW (32 / ICP_NW)              // reduction outputs summed by each warp
 #define ICP_SMEM_BYTES (32 * ICP_THREADS * sizeof(float))
-__global__ void __launch_bounds__(ICP_THREADS, 512 / ICP_THREADS) k_icp(IcpParams p) {
+__global__ void __launch_bounds__(ICP_THREADS, 512 / ICP_THREADS) k_icp(const __grid_constant__ IcpParams p) {
 	__shared__ double sm[ICP_NW][32];
 	extern __shared__ float xs_raw[];       // [32][ICP_THREADS]: per-thread sums, transposed (dynamic: 64 KB at 512 threads)
 	float (*xs)[ICP_THREADS] = reinterpret_cast<float (*)[ICP_THREADS]>(xs_raw);
@@ -595,6 +664,12 @@ __global__ void __launch_bounds__(ICP_THREADS, 512 / ICP_THREADS) k_icp(IcpParam
 	// results to the host, once per frame: sums of the last iteration, final pose, iteration count, then the flag
 	if (blockIdx.x == 0 && wid == 0) {
 		p.out_host[lane] = __ldcg(p.out32 + lane);
+		if (p.tail.out) {
+			// the frame's remaining host algebra, here: checkPoseKernel, inverse(pose), raycastPose * invK
+			if (lane == 0) icp_tail(p);
+			__syncwarp();
+			__threadfence();
+		}
 		if (lane < 16) p.out_host[48 + lane] = __ldcg(p.pose_dev + lane);
 		if (lane == 0) reinterpret_cast<volatile unsigned int*>(p.out_host)[64] = __ldcg(p.bar + 3);
 		__syncwarp();
@@ -613,10 +688,19 @@ __global__ void __launch_bounds__(ICP_THREADS, 512 / ICP_THREADS) k_icp(IcpParam
 // ------------------------------------------------------------------------------------------
 #define BRICK_T 27000
 #define BRICK_SHIFT 3
+#define KFB_MAX_SLABS 8
 struct BrickMap {
-	unsigned char* flag;     // [bnz][bny][bnx]; nullptr = not maintained (multi-slab volumes)
+	unsigned char* flag;     // [bnz][bny][bnx]; nullptr = not maintained
 	uint32_t bnx, bny, bnz;
+	// z-slab mode over peer memory: every rank keeps a map of the WHOLE volume, and a rank that flags a brick of its slab
+	// stores the byte into all peers' maps as well (NVLink P2P; "set to 1" is idempotent, so there is nothing to merge)
+	unsigned char* peer[KFB_MAX_SLABS - 1];
+	int n_peer;
 };
+__device__ __forceinline__ void brick_set(const BrickMap& b, size_t idx) {
+	b.flag[idx] = 1;
+	for (int i = 0; i < b.n_peer; ++i) b.peer[i][idx] = 1;
+}
 __device__ __noinline__ void brick_mark(const BrickMap b, uint32_t x, uint32_t y, uint32_t z) {
 	const uint32_t bx1 = x >> BRICK_SHIFT, by1 = y >> BRICK_SHIFT, bz1 = z >> BRICK_SHIFT;
 	const uint32_t bx0 = (((x & 7u) == 0u) && x) ? bx1 - 1 : bx1, by0 = (((y & 7u) == 0u) && y) ? by1 - 1 : by1,
@@ -624,8 +708,8 @@ __device__ __noinline__ void brick_mark(const BrickMap b, uint32_t x, uint32_t y
 	for (uint32_t bz = bz0; bz <= bz1; ++bz)
 		for (uint32_t by = by0; by <= by1; ++by)
 			for (uint32_t bx = bx0; bx <= bx1; ++bx) {
-				unsigned char* f = b.flag + ((size_t) bz * b.bny + by) * b.bnx + bx;
-				if (*f == 0) *f = 1;
+				const size_t idx = ((size_t) bz * b.bny + by) * b.bnx + bx;
+				if (b.flag[idx] == 0) brick_set(b, idx);
 			}
 }
 // rebuild from a volume (after kfb_write_buffer / for tests)
@@ -673,6 +757,7 @@ struct IntegrateParams {
 	uint32_t zchunk;           // z-steps per blockIdx.z
 	const float* depth; uint32_t dw, dh;
 	Mat4 invTrack, K;
+	const DevFrame* dev;       // optional: invTrack (and the integrate gate) come from the ICP kernel's tail instead
 	float mu, maxweight;
 	const float* dmax;         // optional: max of the depth image (device scalar); nullptr = unknown
 	int cull;                  // 0 = visit every voxel (debug / A-B), 1 = interval + fast tests
@@ -735,16 +820,17 @@ __device__ __noinline__ float integrate_exact_sdf(float Px, float Py, float Pz, 
 
 // per-column state at z = 0 (cpp/kernels.cpp:638-644) and the conservative visited interval of one column
 struct IntColumn { float3 pos0, cam0, delta, cameraDelta; };
-__device__ __forceinline__ IntColumn int_column(const IntegrateParams& p, uint32_t x, uint32_t y) {
+__device__ __forceinline__ IntColumn int_column(const IntegrateParams& p, const Mat4& invTrack, uint32_t x, uint32_t y) {
 	IntColumn c;
-	c.delta = mat_rotate(p.invTrack, f3(0, 0, p.dz / (float) p.sz));
+	c.delta = mat_rotate(invTrack, f3(0, 0, p.dz / (float) p.sz));
 	c.cameraDelta = mat_rotate(p.K, c.delta);
 	// Volume::pos (commons.h:186-189) at z = 0
-	c.pos0 = mat_point(p.invTrack, f3(((float) x + 0.5f) * p.dx / (float) p.sx, ((float) y + 0.5f) * p.dy / (float) p.sy,
+	c.pos0 = mat_point(invTrack, f3(((float) x + 0.5f) * p.dx / (float) p.sx, ((float) y + 0.5f) * p.dy / (float) p.sy,
 			(0 + 0.5f) * p.dz / (float) p.sz));
 	c.cam0 = mat_point(p.K, c.pos0);
 	return c;
 }
+__device__ __forceinline__ IntColumn int_column(const IntegrateParams& p, uint32_t x, uint32_t y) { return int_column(p, p.invTrack, x, y); }
 
 // Pass 1: one warp per 32 x-adjacent columns: conservative interval, appended to the work list.
 // entry = { xtile | y << 16, za | zb << 16 } plus a zeroed piece counter.
@@ -909,7 +995,7 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run(Integr
 						const uint32_t by1 = y >> BRICK_SHIFT, by0 = (((y & 7u) == 0u) && y) ? by1 - 1 : by1;
 						const uint32_t bz1 = (uint32_t) z >> BRICK_SHIFT, bz0 = (first && bz1) ? bz1 - 1 : bz1;
 						for (uint32_t bz = bz0; bz <= bz1; ++bz)
-							for (uint32_t by = by0; by <= by1; ++by) p.brick.flag[((size_t) bz * p.brick.bny + by) * p.brick.bnx + bx] = 1;
+							for (uint32_t by = by0; by <= by1; ++by) brick_set(p.brick, ((size_t) bz * p.brick.bny + by) * p.brick.bnx + bx);
 					}
 				}
 			}
@@ -937,7 +1023,6 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run(Integr
 // does.  The volume may be split into z-slabs owned by different GPUs: slab s holds
 // z in [slab_z[s], slab_z[s+1]) at slab_ptr[s] (peer memory over NVLink when s is remote).
 // ------------------------------------------------------------------------------------------
-#define KFB_MAX_SLABS 8
 struct VolView {
 	const short2* slab_ptr[KFB_MAX_SLABS];
 	uint32_t slab_z[KFB_MAX_SLABS + 1];
@@ -1114,6 +1199,10 @@ struct RaycastParams {
 	uint32_t w, h;
 	uint32_t row0, row1;            // rows handled by this context (multi-GPU: a band of pixels)
 	Mat4 view;
+	const float* view_dev;          // optional: the view matrix comes from the ICP kernel's tail (DevFrame::view)
+	// z-slab mode over peer memory: this rank's band of pixels is also stored into every peer's maps (the all-gather, fused)
+	float* peer_vertex[KFB_MAX_SLABS - 1]; float* peer_normal[KFB_MAX_SLABS - 1];
+	int n_peer;
 	float nearPlane, farPlane, step, largestep;
 	unsigned int* tile_next;        // dynamic tile counter of this launch; tile_reset is zeroed for the next one
 	unsigned int* tile_reset;
@@ -1129,6 +1218,11 @@ struct RaycastParams {
 __global__ void __launch_bounds__(RCK_BX* RCK_BY) k_raycast(RaycastParams p) {
 	const uint32_t lane = threadIdx.x & 31;
 	if (blockIdx.x == 0 && threadIdx.x == 0) *p.tile_reset = 0u;
+	Mat4 view = p.view;
+	if (p.view_dev) {
+#pragma unroll
+		for (int i = 0; i < 16; ++i) view.m[i] = __ldg(p.view_dev + i);
+	}
 	const uint32_t tiles_x = (p.w + 7) / 8, tiles_y = (p.row1 - p.row0 + 3) / 4, tiles = tiles_x * tiles_y;
 	for (;;) {
 		uint32_t t = 0;
@@ -1141,15 +1235,20 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY) k_raycast(RaycastParams p) {
 		if (x < p.w && y < p.row1) {
 			const size_t idx = (size_t) x + (size_t) y * p.w;
 			float hw;
-			const float3 hit = raycast_one(p.vol, x, y, p.view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw);
+			const float3 hit = raycast_one(p.vol, x, y, view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw);
+			float3 nrm = f3(KFB_INVALID, 0, 0);
+			bool nrm_x_only = false;        // zero gradient: the reference writes only normal.x (:745)
 			if (hw > 0.0f) {
-				st3(p.vertex, idx, hit);
 				const float3 surfNorm = vol_grad(p.vol, hit);
-				if (klength(surfNorm) == 0) p.normal[3 * idx] = KFB_INVALID;  // only .x (:745)
-				else st3(p.normal, idx, knormalize(surfNorm));
-			} else {
-				st3(p.vertex, idx, f3(0, 0, 0));
-				st3(p.normal, idx, f3(KFB_INVALID, 0, 0));
+				if (klength(surfNorm) == 0) nrm_x_only = true;
+				else nrm = knormalize(surfNorm);
+			}
+			const float3 vtx = hw > 0.0f ? hit : f3(0, 0, 0);
+			st3(p.vertex, idx, vtx);
+			if (nrm_x_only) p.normal[3 * idx] = KFB_INVALID; else st3(p.normal, idx, nrm);
+			for (int i = 0; i < p.n_peer; ++i) {
+				st3(p.peer_vertex[i], idx, vtx);
+				if (nrm_x_only) p.peer_normal[i][3 * idx] = KFB_INVALID; else st3(p.peer_normal[i], idx, nrm);
 			}
 		}
 		if (p.tile_cost) {   // diagnostics (KFB_RAY_TILECOST=1): how long this tile kept its warp
@@ -1231,6 +1330,32 @@ __global__ void __launch_bounds__(RC_BX* RC_BY) k_render_volume(RenderVolumePara
 		}
 	}
 	p.out[(size_t) x + (size_t) y * p.w] = o;
+}
+
+// ------------------------------------------------------------------------------------------
+// Stream-ordered barrier between the ranks of a z-slab group, over peer memory (no NCCL): barrier number `n` is complete
+// for this rank when every peer has stored n into this rank's arrival slots.  One thread per rank.  Everything this rank
+// wrote before (its slab, the flags and map bands it stored into peers) is fenced system-wide before its arrival is
+// published; a peer that never arrives is reported after ~4 s instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------
+struct PeerSync { unsigned int arrive[KFB_MAX_SLABS]; };
+struct PeerSyncTable { PeerSync* p[KFB_MAX_SLABS]; };
+__global__ void k_peer_barrier(PeerSyncTable all, int rank, int world, unsigned int n, volatile unsigned int* err_host) {
+	const int r = threadIdx.x;
+	if (r >= world) return;
+	__threadfence_system();
+	if (r != rank) {
+		asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(&all.p[r]->arrive[rank]), "r"(n) : "memory");
+		const unsigned long long t0 = gtime_ns();
+		unsigned int v;
+		for (;;) {
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&all.p[rank]->arrive[r]) : "memory");
+			if ((int) (v - n) >= 0) break;
+			__nanosleep(100);
+			if (gtime_ns() - t0 > 4000000000ull) { if (err_host) *err_host = 0x100u + (unsigned int) r; break; }
+		}
+	}
+	__threadfence_system();
 }
 
 // dumpVolume helper (cpp/kernels.cpp:1022-1026): gather the tsdf shorts

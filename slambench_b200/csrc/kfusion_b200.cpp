@@ -121,10 +121,17 @@ bool Kfusion::integration(float4 k, uint integration_rate, float mu, uint frame)
 
 void Kfusion::computeFrame(const ushort* inputDepth, const uint2 inputSize, float4 k, uint integration_rate, uint tracking_rate,
 		float icp_threshold, float mu, const uint frame) {
-	preprocessing(inputDepth, inputSize);
-	_tracked = tracking(k, icp_threshold, tracking_rate, frame);
-	_integrated = integration(k, integration_rate, mu, frame);
-	raycasting(k, mu, frame);
+	// one C-ABI call: the library enqueues the whole frame before it waits for the pose (kfb_compute_frame)
+	kfb_ctx* c = ctx_of(this);
+	float kk[4];
+	k4(k, kk);
+	int tracked = 0, integrated = 0;
+	const int rc = kfb_compute_frame(c, inputDepth, inputSize.x, inputSize.y, kk, integration_rate, tracking_rate, icp_threshold, mu, frame,
+			&tracked, &integrated);
+	check(rc, "kfb_compute_frame");
+	check(kfb_get_pose(c, reinterpret_cast<float*>(&pose)), "kfb_get_pose");
+	_tracked = tracked != 0;
+	_integrated = integrated != 0;
 }
 
 void Kfusion::dumpVolume(const char* filename) {

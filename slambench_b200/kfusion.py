@@ -55,6 +55,12 @@ class KfbStats(C.Structure):
     ]
 
 
+class KfbIpcHandles(C.Structure):
+    _fields_ = [("volume", C.c_uint8 * 64), ("vertex", C.c_uint8 * 64), ("normal", C.c_uint8 * 64), ("bricks", C.c_uint8 * 64),
+                ("sync", C.c_uint8 * 64), ("has_bricks", C.c_uint32), ("slab_z0", C.c_uint32), ("slab_z1", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
 class KfbError(RuntimeError):
     pass
 
@@ -203,6 +209,14 @@ class Kfusion:
         self._check(self.lib.kfb_compute_frame(self._h, _p(d), C.c_uint32(w), C.c_uint32(h), _p(_f32(k, 4)), C.c_uint32(integration_rate),
                                                C.c_uint32(tracking_rate), C.c_float(icp_threshold), C.c_float(mu), C.c_uint32(frame),
                                                C.byref(tr), C.byref(it)))
+        self._tracked, self._integrated = bool(tr.value), bool(it.value)
+
+    def computeFrame_device(self, dev_ptr: int, inputSize, k, integration_rate, tracking_rate, icp_threshold, mu, frame):
+        """computeFrame for a uint16 sensor frame already resident in device memory (raw pointer)."""
+        tr, it = C.c_int(0), C.c_int(0)
+        self._check(self.lib.kfb_compute_frame_device(self._h, C.c_void_p(dev_ptr), C.c_uint32(inputSize[0]), C.c_uint32(inputSize[1]),
+                                                      _p(_f32(k, 4)), C.c_uint32(integration_rate), C.c_uint32(tracking_rate),
+                                                      C.c_float(icp_threshold), C.c_float(mu), C.c_uint32(frame), C.byref(tr), C.byref(it)))
         self._tracked, self._integrated = bool(tr.value), bool(it.value)
 
     def getTracked(self) -> bool:
@@ -363,6 +377,20 @@ class Kfusion:
     # ---------------------------------------------------------------- multi-GPU
     def set_pixel_rows(self, row0: int, row1: int):
         self._check(self.lib.kfb_set_pixel_rows(self._h, C.c_uint32(row0), C.c_uint32(row1)))
+
+    def ipc_export(self) -> bytes:
+        """This context's slab, raycast maps, brick flags and barrier slot as CUDA IPC handles (kfb_ipc_handles, 336 bytes)."""
+        h = KfbIpcHandles()
+        self._check(self.lib.kfb_ipc_export(self._h, C.byref(h)))
+        return bytes(h)
+
+    def ipc_import(self, rank: int, world: int, handles: list[bytes]):
+        """Enter the peer-memory z-slab mode: `handles[r]` = rank r's ipc_export()."""
+        arr = (KfbIpcHandles * world).from_buffer_copy(b"".join(handles))
+        self._check(self.lib.kfb_ipc_import(self._h, C.c_int(rank), C.c_int(world), arr))
+
+    def peer_barrier(self):
+        self._check(self.lib.kfb_peer_barrier(self._h))
 
     def slab_ipc_handle(self) -> bytes:
         buf = (C.c_uint8 * 64)()

@@ -21,10 +21,13 @@ the single-GPU C ABI (include/kfb200.h):
               control flow, cpp/kernels.cpp:950-969).
   preprocess  replicated (614 KB of input per rank; cheaper than exchanging).
 
-Ordering between ranks is stream-ordered: a 1-element all-reduce after integrate (nobody raycasts a
-peer's slab before that peer has integrated the frame) and the all-gather after raycast (nobody
-integrates the next frame while a peer still reads its slab).  All collectives are enqueued on the
-context's own CUDA stream.
+Transport.  "peer" (default): after one exchange of CUDA-IPC handles the library moves every per-frame
+byte itself over NVLink peer memory — k_integrate_run2 stores the brick flags of its slab into every peer's
+map, k_raycast stores its band of the vertex / normal maps into every peer's maps (the all-gather, fused into
+the kernel), and kfb_integrate / kfb_raycast end with a stream-ordered barrier over peer memory
+(k_peer_barrier): no NCCL collective per frame in the replicated ICP mode.  "nccl": round 1's data path
+(flags all-reduced, bands all-gathered), kept for A/B.  Ordering: nobody raycasts a peer's slab before that
+peer has integrated the frame; nobody integrates the next frame while a peer still reads its slab.
 """
 from __future__ import annotations
 
@@ -139,7 +142,7 @@ class ShardedKfusion:
 
     def __init__(self, inputSize, volumeResolution, volumeDimensions, initPose, pyramid=(10, 5, 4), *, rank: int, world: int,
                  device: int = 0, icp_mode: str = "replicated", dist=None, local_factory=None, flags: int = 0,
-                 balance_k=None, balance_far: float = 4.0):
+                 balance_k=None, balance_far: float = 4.0, transport: str = "peer"):
         if dist is None:
             import torch.distributed as dist  # noqa: PLC0415
         import torch  # noqa: PLC0415
@@ -148,6 +151,8 @@ class ShardedKfusion:
         self.rank, self.world, self.device = rank, world, device
         if icp_mode not in ("replicated", "allreduce"):
             raise ValueError(icp_mode)
+        if transport not in ("peer", "nccl"):
+            raise ValueError(transport)
         self.icp_mode = icp_mode
         vr = [int(volumeResolution)] * 3 if np.isscalar(volumeResolution) else [int(v) for v in volumeResolution]
         weights = None
@@ -164,10 +169,19 @@ class ShardedKfusion:
         make = local_factory or (lambda **kw: kf.Kfusion(inputSize, vr, volumeDimensions, initPose, self.pyramid, **kw))
         self.local = make(device=device, slab=self.slabs[rank], flags=flags | kf.FLAG_BRICKS_MERGED)
         self.computationSize = (int(inputSize[0]), int(inputSize[1]))
-        # peer slabs: CUDA IPC handles travel through the (CPU) object collective
+        # CUDA IPC handles travel through the (CPU) object collective, once.  "peer" (default): slabs, raycast maps, brick
+        # flags and barrier slots are all exchanged — the library then moves every per-frame byte itself over NVLink peer
+        # memory (flags and map bands stored straight into the peers, barriers in kfb_integrate / kfb_raycast) and this
+        # class issues NO collective per frame in the replicated ICP mode.  "nccl": round 1's data path (peer loads of
+        # the slabs only; flags all-reduced and bands all-gathered by NCCL), kept for A/B runs.
+        self.transport = transport if hasattr(self.local, "ipc_export") else "nccl"
         handles = [None] * world
-        dist.all_gather_object(handles, self.local.slab_ipc_handle())
-        self.local.slab_import(rank, world, handles, [z[0] for z in self.slabs])
+        if self.transport == "peer":
+            dist.all_gather_object(handles, self.local.ipc_export())
+            self.local.ipc_import(rank, world, handles)
+        else:
+            dist.all_gather_object(handles, self.local.slab_ipc_handle())
+            self.local.slab_import(rank, world, handles, [z[0] for z in self.slabs])
         self.local.set_pixel_rows(*self.bands[rank])
         self._stream = self.local.torch_stream(torch) if hasattr(self.local, "torch_stream") else None
         w, h = self.computationSize
@@ -238,6 +252,8 @@ class ShardedKfusion:
 
     def integration(self, k, integration_rate: int, mu: float, frame: int) -> bool:
         done = self.local.integration(k, integration_rate, mu, frame)
+        if self.transport == "peer":
+            return done                                  # flags already stored into the peers; barrier inside kfb_integrate
         with self._on_stream():
             # stream-ordered barrier (every slab holds this frame before any peer reads it) that also merges the
             # brick flags: a rank flags only the bricks ITS slices touch; the raycaster needs the union
@@ -249,7 +265,7 @@ class ShardedKfusion:
 
     def raycasting(self, k, mu: float, frame: int) -> bool:
         self.local.raycasting(k, mu, frame)          # this rank's row band, through all slabs (peer loads)
-        if frame > 2:
+        if frame > 2 and self.transport != "peer":       # "peer": bands already stored into the peers; barrier inside kfb_raycast
             r0, r1 = self.bands[self.rank]
             with self._on_stream():
                 self.dist.all_gather_into_tensor(self._vertex, self._vertex[r0:r1])

@@ -289,14 +289,90 @@ def test_odd_configurations(port, seq16, res, dim, csize, pyr, pose_tol):
     assert ((a[4][..., 0] != -2) == (nrm_c[..., 0] != -2)).mean() > 0.99
 
 
-def test_compute_frame_entry_point(seq16):
-    """kfb_compute_frame == preprocessing + tracking + integration + raycasting (cpp/kernels.cpp:1048-1055)."""
+@pytest.mark.parametrize("rates", [(1, 1), (2, 3)])
+def test_compute_frame_entry_point(seq16, rates):
+    """kfb_compute_frame == preprocessing + tracking + integration + raycasting (cpp/kernels.cpp:1048-1055), bit for bit:
+    the whole-frame enqueue (checkPose / inverse(pose) / raycastPose * invK evaluated by the ICP kernel's last CTA, integrate
+    gated on the device) must leave the same poses, flags, volume and raycast maps as the staged calls, including frames
+    where tracking or integration is skipped by its rate and a frame where tracking is lost."""
+    depth, _ = seq16
+    irate, trate = rates
+    n = 10
+    lost = depth[7].copy()
+    lost[:] = 600                                  # a wall 0.6 m away: ICP cannot explain it -> tracking lost, pose restored
+    frames = [lost if f == 7 else depth[f] for f in range(n)]
+    res = []
+    for one_call in (False, True):
+        with kf.Kfusion((640, 480), 96, 4.8, T0, (10, 5, 4)) as g:
+            out = []
+            for f in range(n):
+                if one_call:
+                    g.computeFrame(frames[f], None, K, irate, trate, 1e-5, 0.1, f)
+                    tr, it = g.getTracked(), g.getIntegrated()
+                else:
+                    g.preprocessing(frames[f])
+                    tr = g.tracking(K, 1e-5, trate, f)
+                    it = g.integration(K, irate, 0.1, f)
+                    g.raycasting(K, 0.1, f)
+                out.append((tr, it, g.getPose().copy()))
+            res.append((out, g.read(kf.BUF_VOLUME), g.read(kf.BUF_VERTEX), g.read(kf.BUF_NORMAL), g.read(kf.BUF_RAYCASTPOSE),
+                        g.stats()["frames_integrated"]))
+            if one_call:
+                assert np.array_equal(g.getPosition(), g.getPose()[:3, 3] - T0)
+    (a, va, xa, na, ra, ca), (b, vb, xb, nb, rb, cb_) = res
+    for f in range(n):
+        assert a[f][:2] == b[f][:2], f"frame {f}: flags {b[f][:2]} != staged {a[f][:2]}"
+        assert np.array_equal(a[f][2], b[f][2]), f"frame {f}: pose differs"
+    if rates == (1, 1):
+        assert a[7][0] is False and a[6][0] is True, "the tracking-loss frame was not exercised"
+    assert np.array_equal(va, vb) and np.array_equal(xa, xb) and np.array_equal(na, nb) and np.array_equal(ra, rb)
+    assert ca == cb_ == sum(x[1] for x in a)
+
+
+@pytest.mark.parametrize("pyr", [(4, 3, 3, 2, 2), (3, 0, 2, 2)])
+def test_more_than_three_pyramid_levels(port, seq16, pyr):
+    """The reference accepts any `-y` list (default_parameters.h:394-396): 4 and 5 levels, and a level with no iterations."""
     depth, _ = seq16
     n = 8
-    pa, ta, ia = run_gpu_pipeline(depth, n, 96)
-    with kf.Kfusion((640, 480), 96, 4.8, T0, (10, 5, 4)) as g:
+    pc, tc, ic = run_cpu_pipeline(port, depth, n, 64, pyramid=pyr)
+    pg, tg, ig = run_gpu_pipeline(depth, n, 64, pyramid=pyr)
+    assert tg == tc and ig == ic
+    assert any(tc), "nothing tracked: the configuration does not exercise the deeper levels"
+    for f in range(n):
+        assert np.abs(pg[f] - pc[f]).max() <= 1e-4, f"frame {f}"
+    # the deepest level's maps, teacher-forced: bit-exact
+    with kf.Kfusion((640, 480), 64, 4.8, T0, pyr) as g:
+        g.preprocessing(depth[5])
+        g.pyramidKernels(K)
+        lvl = len(pyr) - 1
+        raw = port.mm2meters(depth[5], (640, 480))
+        d = port.bilateral(raw, port.gaussian())
+        for _ in range(lvl):
+            d = port.halfsample(d)
+        assert np.array_equal(g.read(kf.BUF_SCALEDDEPTH, lvl), d)
+        v = port.depth2vertex(d, port.inverse_camera_matrix(K / np.float32(1 << lvl)))
+        assert np.array_equal(g.read(kf.BUF_INVERTEX, lvl), v)
+        nrm = port.vertex2normal(v)
+        got = g.read(kf.BUF_INNORMAL, lvl)
+        valid = nrm[..., 0] != -2
+        assert np.array_equal(got[..., 0] == -2, ~valid) and np.array_equal(got[valid], nrm[valid])
+
+
+def test_compute_size_ratio_8(port, seq16):
+    """`-c 8` (default_parameters.h:274-277): 80x60 computation size from the 640x480 sensor frame, whole pipeline."""
+    depth, _ = seq16
+    n, k8 = 8, (K / np.float32(8)).astype(np.float32)
+    pc, tc, ic = run_cpu_pipeline(port, depth, n, 64, csize=(80, 60), k=k8)
+    poses, tr, it = [], [], []
+    with kf.Kfusion((80, 60), 64, 4.8, T0, (10, 5, 4)) as g:
         for f in range(n):
-            g.computeFrame(depth[f], None, K, 1, 1, 1e-5, 0.1, f)
-            assert (g.getTracked(), g.getIntegrated()) == (ta[f], ia[f])
-            assert np.array_equal(g.getPose(), pa[f])
-        assert np.array_equal(g.getPosition(), g.getPose()[:3, 3] - T0)
+            g.preprocessing(depth[f])
+            tr.append(g.tracking(k8, 1e-5, 1, f))
+            it.append(g.integration(k8, 1, 0.1, f))
+            g.raycasting(k8, 0.1, f)
+            poses.append(g.getPose().copy())
+        raw = port.mm2meters(depth[n - 1], (80, 60))
+        assert np.array_equal(g.read(kf.BUF_FLOATDEPTH), raw)
+    assert tr == tc and it == ic
+    for f in range(n):
+        assert np.abs(poses[f] - pc[f]).max() <= 1e-4, f"frame {f}"
