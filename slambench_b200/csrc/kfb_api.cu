@@ -406,6 +406,7 @@ static int create_impl(const kfb_config* cfg, kfb_ctx* c) {
 	c->view_all.sx = cfg->volume_res[0]; c->view_all.sy = cfg->volume_res[1]; c->view_all.sz = cfg->volume_res[2];
 	c->view_all.dx = cfg->volume_dim[0]; c->view_all.dy = cfg->volume_dim[1]; c->view_all.dz = cfg->volume_dim[2];
 	c->view_all.rdx = 1.0f / cfg->volume_dim[0]; c->view_all.rdy = 1.0f / cfg->volume_dim[1]; c->view_all.rdz = 1.0f / cfg->volume_dim[2];
+	{ const char* e = getenv("KFB_RAY_NO_LEAP"); c->view_all.no_leap = (e && atoi(e) > 0) ? 1 : 0; }
 	c->view_all.fastdiv = (kfb_fastdiv_ok(cfg->volume_dim[0]) && kfb_fastdiv_ok(cfg->volume_dim[1]) && kfb_fastdiv_ok(cfg->volume_dim[2])) ? 1 : 0;
 	const bool whole = (c->z0 == 0 && c->z1 == cfg->volume_res[2]);
 	if ((whole || (c->cfg.flags & KFB_FLAG_BRICKS_MERGED)) && !(c->cfg.flags & KFB_FLAG_RAYCAST_NO_SKIP)) {

@@ -1035,6 +1035,7 @@ struct VolView {
 	int fastdiv;
 	const unsigned char* brick;   // brick flags (see BrickMap) or nullptr
 	uint32_t bnx, bny;
+	int no_leap;                  // A/B switch (KFB_RAY_NO_LEAP=1): take every fine step through clear bricks one by one
 };
 
 // fl(a / d) for a per-launch constant d with rd = fl(1/d): q = a*rd, r = fma(-d, q, a) (exact), q + r*rd rounds
@@ -1171,9 +1172,33 @@ __device__ __forceinline__ float3 raycast_one(const VolView& v, uint32_t px, uin
 			// f_t of the zero crossing: it is then evaluated at the remembered t (same expression, same value).
 			bool lazy = false;
 			float t_lazy = t;
+			const bool leap = !v.no_leap;
 			for (; t < tfar; t += stepsize) {
 				const VolCell c = vol_cell(v, origin + direction * t);
-				if (vol_cell_free(v, c)) { f_tt = 1.f; lazy = true; t_lazy = t; continue; }
+				if (vol_cell_free(v, c)) {
+					f_tt = 1.f; lazy = true; t_lazy = t;
+					// Fine steps (one voxel each) inside a clear brick: the next samples whose base voxel provably stays in
+					// THIS brick are clear as well, so only the reference's `t += stepsize` is replayed for them (the exact
+					// sequence of t values is kept; nothing else depends on those samples).  A ray that has grazed a surface
+					// walks the rest of its way in fine steps: these are the longest chains of the kernel.
+					if (leap && stepsize == step && c.bx >= 0 && c.by >= 0 && c.bz >= 0 && c.bx < (int) v.sx - 1 && c.by < (int) v.sy - 1 && c.bz < (int) v.sz - 1) {
+						// voxels per unit t along each axis, and the room (in t) to the brick's faces, shrunk by a margin that
+						// dwarfs every rounding involved (positions are exact to ~1e-3 voxel)
+						const float3 ds = f3(direction.x * ((float) v.sx * v.rdx), direction.y * ((float) v.sy * v.rdy), direction.z * ((float) v.sz * v.rdz));
+						const float px_ = (float) (c.bx & 7) + c.fx, py_ = (float) (c.by & 7) + c.fy, pz_ = (float) (c.bz & 7) + c.fz;   // position inside the brick, [0, 8)
+						const float rx = (ds.x > 0.f ? 7.95f - px_ : px_ - 0.05f) * rcp_approx(fabsf(ds.x) + 1e-20f);
+						const float ry = (ds.y > 0.f ? 7.95f - py_ : py_ - 0.05f) * rcp_approx(fabsf(ds.y) + 1e-20f);
+						const float rz = (ds.z > 0.f ? 7.95f - pz_ : pz_ - 0.05f) * rcp_approx(fabsf(ds.z) + 1e-20f);
+						const float room = kminf(kminf(rx, ry), rz);
+						int n = (room > 0.f) ? (int) kminf(room * rcp_approx(stepsize), 64.f) - 1 : 0;
+						while (n > 0) {
+							const float tn = t + stepsize;
+							if (!(tn < tfar)) break;   // the loop's own increment and test end the march
+							t = tn; t_lazy = tn; --n;
+						}
+					}
+					continue;
+				}
 				f_tt = vol_interp_cell(v, c);
 				if (f_tt < 0) break;
 				if (f_tt < 0.8f) stepsize = step;
@@ -1215,14 +1240,15 @@ struct RaycastParams {
 #define RCK_BY 4
 // Persistent warps pull 8x4-pixel tiles from a counter: rays differ a lot in length (near objects vs the far wall),
 // and with a static grid the last wave leaves most SMs idle.
-__global__ void __launch_bounds__(RCK_BX* RCK_BY) k_raycast(RaycastParams p) {
+#ifndef KFB_RAY_MINBLOCKS
+#define KFB_RAY_MINBLOCKS 9   // 56 registers: the kernel needs its warps (measured in round 1: monotonically faster up to 9 CTAs / SM)
+#endif
+__global__ void __launch_bounds__(RCK_BX* RCK_BY, KFB_RAY_MINBLOCKS) k_raycast(RaycastParams p) {
 	const uint32_t lane = threadIdx.x & 31;
 	if (blockIdx.x == 0 && threadIdx.x == 0) *p.tile_reset = 0u;
-	Mat4 view = p.view;
-	if (p.view_dev) {
-#pragma unroll
-		for (int i = 0; i < 16; ++i) view.m[i] = __ldg(p.view_dev + i);
-	}
+	__shared__ Mat4 view;   // by value from the host, or from the ICP kernel's tail (shared memory: no registers held for it)
+	if (threadIdx.x < 16) view.m[threadIdx.x] = p.view_dev ? __ldg(p.view_dev + threadIdx.x) : p.view.m[threadIdx.x];
+	__syncthreads();
 	const uint32_t tiles_x = (p.w + 7) / 8, tiles_y = (p.row1 - p.row0 + 3) / 4, tiles = tiles_x * tiles_y;
 	for (;;) {
 		uint32_t t = 0;
@@ -1236,19 +1262,20 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY) k_raycast(RaycastParams p) {
 			const size_t idx = (size_t) x + (size_t) y * p.w;
 			float hw;
 			const float3 hit = raycast_one(p.vol, x, y, view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw);
-			float3 nrm = f3(KFB_INVALID, 0, 0);
-			bool nrm_x_only = false;        // zero gradient: the reference writes only normal.x (:745)
 			if (hw > 0.0f) {
+				st3(p.vertex, idx, hit);
 				const float3 surfNorm = vol_grad(p.vol, hit);
-				if (klength(surfNorm) == 0) nrm_x_only = true;
-				else nrm = knormalize(surfNorm);
+				if (klength(surfNorm) == 0) p.normal[3 * idx] = KFB_INVALID;  // only .x (:745)
+				else st3(p.normal, idx, knormalize(surfNorm));
+			} else {
+				st3(p.vertex, idx, f3(0, 0, 0));
+				st3(p.normal, idx, f3(KFB_INVALID, 0, 0));
 			}
-			const float3 vtx = hw > 0.0f ? hit : f3(0, 0, 0);
-			st3(p.vertex, idx, vtx);
-			if (nrm_x_only) p.normal[3 * idx] = KFB_INVALID; else st3(p.normal, idx, nrm);
-			for (int i = 0; i < p.n_peer; ++i) {
-				st3(p.peer_vertex[i], idx, vtx);
-				if (nrm_x_only) p.peer_normal[i][3 * idx] = KFB_INVALID; else st3(p.peer_normal[i], idx, nrm);
+			if (p.n_peer) {
+				// z-slab group: the pixel as it now stands in this rank's maps (including the components an x-only normal write
+				// left from the previous frame: the owner of a pixel never changes) goes to every peer
+				const float3 vv = ld3(p.vertex, idx), nn = ld3(p.normal, idx);
+				for (int i = 0; i < p.n_peer; ++i) { st3(p.peer_vertex[i], idx, vv); st3(p.peer_normal[i], idx, nn); }
 			}
 		}
 		if (p.tile_cost) {   // diagnostics (KFB_RAY_TILECOST=1): how long this tile kept its warp
