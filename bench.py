@@ -196,6 +196,33 @@ def run_cpu_frames(depth, vres: int, n_warm: int, n_timed: int, budget_s: float 
     return done, t_sum, kind, cores, be.name
 
 
+def run_reference_cuda(depth, vres: int, n_frames: int):
+    """GPU comparator: the reference's OWN CUDA backend (kfusion/src/cuda/kernels.cu, unmodified, compiled for sm_100a into
+    oracle/_ref/kfusion-benchmark-cuda) on the same frames, on this GPU.  fps from the `computation` column over frames >= 4
+    (benchmark.cpp:166), i.e. with its own per-stage synchronisation.  None when the binary was not built."""
+    import tempfile
+
+    from oracle import cpu_backend as cb
+    from slambench_b200 import synth
+
+    if not os.path.exists(cb.REF_CUDA_BIN):
+        return None
+    with tempfile.TemporaryDirectory() as tmp:
+        raw, log = os.path.join(tmp, "seq.raw"), os.path.join(tmp, "cuda.log")
+        synth.write_raw(raw, depth[:n_frames])
+        r = subprocess.run([cb.REF_CUDA_BIN, "-i", raw, "-s", "4.8", "-p", "0.5,0.5,0.25", "-z", "1000000", "-c", "1", "-r", "1", "-t", "1",
+                            "-m", "0.1", "-y", "10,5,4", "-k", "481.2,480,320,240", "-v", str(vres), "-o", log],
+                           stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, timeout=300)
+        if r.returncode != 0 or not os.path.exists(log):
+            return {"unavailable": f"kfusion-benchmark-cuda exited {r.returncode}: {r.stderr.decode(errors='replace')[-200:]}"}
+        rows = np.array([[float(v) for v in l.split()] for l in open(log) if len(l.split()) == 14 and l.split()[0].isdigit()])
+    t = rows[4:]
+    return {"value": float(1.0 / t[:, 7].mean()), "unit": UNIT, "kind": "reference-cuda (kfusion/src/cuda/kernels.cu, unmodified, sm_100a)",
+            "stage_ms_per_frame": {"preprocess": 1e3 * float(t[:, 2].mean()), "track": 1e3 * float(t[:, 3].mean()),
+                                   "integrate": 1e3 * float(t[:, 4].mean()), "raycast": 1e3 * float(t[:, 5].mean())},
+            "tracked_frames": int(t[:, 12].sum()), "sample": f"{len(t)} frames (from frame 4) of the same sequence and volume"}
+
+
 def reference_arm(args, rank: int):
     """`--impl reference`: the reference's own CPU implementation of the path on this box's cores."""
     if rank != 0:
@@ -382,6 +409,10 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
                                                      args.cpu_budget / 2, single_thread=True)
             line["cpu_baseline"]["cpp_1thread"] = {"value": d1 / s1, "unit": UNIT, "cores": 1, "kind": kind1, "backend": name1,
                                                    "sample": f"{d1} frames (from frame {min(4, args.warmup)}), bounded to ~{args.cpu_budget / 2:.0f} s"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        gb = run_reference_cuda(depth_np, args.volume, min(n, 40))
+        if gb is not None:
+            line["gpu_baseline"] = gb
     sh = None
     if dist is not None and not args.no_sharded:
         # N > 1: the driver only ever runs `bench.py --gpus N`, so the z-slab mode (BASELINE configs[3]: ONE sequence,

@@ -59,7 +59,8 @@ typedef struct kfb_stats {
 	uint64_t icp_iterations_last;
 	uint64_t icp_iterations_total;
 	uint64_t h2d_bytes, d2h_bytes;
-	float ms_preprocess, ms_track, ms_integrate, ms_raycast; /* CUDA-event time of the last call of each stage (needs kfb_enable_timing) */
+	float ms_preprocess, ms_track, ms_integrate, ms_raycast; /* CUDA-event time of each stage SUMMED over all calls since
+	                                                            kfb_reset_stats (needs kfb_enable_timing); divide by the call counts */
 } kfb_stats;
 
 /* buffers addressable through kfb_read_buffer / kfb_write_buffer (reference global of the same role,
@@ -95,9 +96,17 @@ int kfb_destroy(kfb_ctx* ctx);
 int kfb_reset(kfb_ctx* ctx);
 
 /* Kfusion::preprocessing(const ushort*, uint2)   cpp/kernels.cpp:915-922.  `depth_mm` is a HOST buffer of the
- * sensor size; the H2D copy is part of the call (asynchronous; the buffer may be reused after kfb_sync or the
- * next kfb_track). */
+ * sensor size; the H2D copy is part of the call.  A PAGEABLE buffer is copied into an internal pinned staging buffer
+ * before the call returns (the caller may reuse it at once, like with the reference).  A PAGE-LOCKED buffer
+ * (cudaHostAlloc / cudaHostRegister / kfb_register_host_buffer; asked from the driver on every call) is read by the copy
+ * engine asynchronously: it may be reused after kfb_sync, or after the next kfb_track / kfb_compute_frame of this context
+ * has returned (both wait for the copy, also on frames that are not tracked). */
 int kfb_preprocess(kfb_ctx* ctx, const uint16_t* depth_mm, uint32_t in_w, uint32_t in_h);
+/* Page-lock a host buffer the caller will pass to kfb_preprocess again and again (benchmark.cpp:103 mallocs ONE frame
+ * buffer) so that its frames are DMA'd directly.  Opt-in: the library never registers a pointer behind the caller's back.
+ * Unregister before freeing the buffer; kfb_destroy unregisters what is left. */
+int kfb_register_host_buffer(kfb_ctx* ctx, const void* ptr, size_t bytes);
+int kfb_unregister_host_buffer(kfb_ctx* ctx, const void* ptr);
 /* same, with the sensor frame already resident in device memory (bench.py's HBM-resident arm) */
 int kfb_preprocess_device(kfb_ctx* ctx, const uint16_t* dev_depth_mm, uint32_t in_w, uint32_t in_h);
 /* Kfusion::tracking(float4 k, float icp_threshold, uint tracking_rate, uint frame)  cpp/kernels.cpp:924-971.

@@ -42,6 +42,19 @@ def build_ref() -> str | None:
     return REF_LIB
 
 
+REF_CUDA_BIN = os.path.join(HERE, "_ref", "kfusion-benchmark-cuda")
+
+
+def build_ref_cuda() -> str | None:
+    """The reference's own CUDA backend, unmodified, compiled for sm_100a (GPU comparator); needs /root/reference + nvcc."""
+    if os.path.isdir(REFERENCE_ROOT):
+        try:
+            subprocess.check_call(["make", "-s", "-C", HERE, "ref_cuda"])
+        except subprocess.CalledProcessError:
+            return None
+    return REF_CUDA_BIN if os.path.exists(REF_CUDA_BIN) else None
+
+
 def have_ref() -> bool:
     return os.path.exists(REF_LIB)
 

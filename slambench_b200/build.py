@@ -82,7 +82,7 @@ def build_benchmark(force: bool = False) -> str | None:
     ref = os.path.join(REFERENCE_ROOT, "kfusion")
     cmd = [
         "g++", "-g", "-O3", "-std=gnu++11", "-w", "-ffp-contract=off",
-        "-I", os.path.join(ROOT, "oracle", "toon_shim"), "-I", os.path.join(ref, "include"),
+        "-I", os.path.join(ROOT, "third_party_shims"), "-I", os.path.join(ref, "include"),
         "-I", os.path.join(ref, "thirdparty"), "-I", os.path.join(ROOT, "include"),
         os.path.join(ref, "src", "benchmark.cpp"), os.path.join(ref, "src", "PowerMonitor.cpp"), glue,
         "-o", BENCH_BIN, "-L", PKG, "-lkfb200", "-Wl,-rpath,$ORIGIN/../slambench_b200", "-lrt", "-lpthread",

@@ -9,10 +9,13 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <vector>
 
 // constant_parameters.h:15-23
@@ -84,7 +87,7 @@ struct kfb_ctx {
 	float* d_inV[KFB_MAX_LEVELS];
 	float* d_inN[KFB_MAX_LEVELS];
 	uint16_t* d_input; size_t input_bytes;
-	uint16_t* h_stage; size_t stage_bytes;
+	uint16_t* h_stage[2]; size_t stage_bytes[2]; cudaEvent_t ev_stage[2]; int stage_cur;   // pinned staging for pageable callers
 	int8_t* d_status;
 	double* d_partials;
 	unsigned int* d_counter;
@@ -100,6 +103,7 @@ struct kfb_ctx {
 	float* h_out32_dev;
 	uint32_t seq;
 	unsigned long long* d_nupd; // NUPD_SLOTS per-integrate counters
+	unsigned long long nupd_folded;   // counts of recycled slots
 	unsigned int* d_dmax;       // three rotating slots: bit pattern of max(floatDepth), written by preprocess
 	uint32_t int_zchunk;        // integrate piece length override (KFB_INT_ZCHUNK, tuning)
 	uint2* d_queue; size_t queue_cap;   // integrate work list
@@ -135,8 +139,8 @@ struct kfb_ctx {
 	PeerSync* d_sync; PeerSyncTable sync_all;
 	unsigned int barrier_count;
 	uint32_t band0, band1;      // pixel rows handled by this context (multi-GPU); whole image by default
-	// registered host pointers (benchmark.cpp reuses one malloc'd frame buffer)
-	const void* reg_ptr[4]; size_t reg_bytes[4]; int n_reg;
+	// host buffers page-locked on the caller's explicit request (kfb_register_host_buffer)
+	const void* reg_ptr[8]; int n_reg;
 	// stats
 	kfb_stats st;
 	uint32_t timing;            // bitmask: 1 preprocess, 2 track, 4 integrate, 8 raycast
@@ -175,6 +179,8 @@ static void timer_free(StageTimer& t) {
 // Is q = a*rd, q + fma(-d,q,a)*rd == a/d for EVERY float a (all 2^23 significands, two binades)?  Checked once per
 // divisor on the host (fmaf is exact); the raycaster then divides by the volume dimensions in 3 instructions.
 static int kfb_fastdiv_ok(float d) {
+	static std::mutex mu;            // contexts may be created from several threads
+	std::lock_guard<std::mutex> lock(mu);
 	static float cache_d[8]; static int cache_r[8]; static int n_cache = 0;
 	for (int i = 0; i < n_cache; ++i) if (cache_d[i] == d) return cache_r[i];
 	int ok = (d == d) && d > 1e-20f && d < 1e20f;
@@ -307,6 +313,7 @@ static int create_impl(const kfb_config* cfg, kfb_ctx* c) {
 	CK(cudaMemsetAsync(c->d_frame, 0, sizeof(DevFrame), c->stream));
 	{ const char* e = getenv("KFB_NO_ASYNC"); c->no_async = e && atoi(e) > 0; }
 	CK(cudaEventCreateWithFlags(&c->ev_h2d, cudaEventDisableTiming));
+	for (int i = 0; i < 2; ++i) { CK(cudaEventCreateWithFlags(&c->ev_stage[i], cudaEventDisableTiming)); CK(cudaEventRecord(c->ev_stage[i], c->stream)); }
 	c->ev_h2d_pending = false;
 	if (getenv("KFB_ICP_PROFILE")) { CK(cudaMalloc(&c->d_icp_prof, 8 * sizeof(unsigned long long))); CK(cudaMemsetAsync(c->d_icp_prof, 0, 8 * sizeof(unsigned long long), c->stream)); }
 	{
@@ -454,6 +461,7 @@ int kfb_destroy(kfb_ctx* c) {
 	if (c->stream) cudaStreamSynchronize(c->stream);
 	if (c->side) cudaStreamSynchronize(c->side);
 	for (int i = 0; i < c->n_reg; ++i) cudaHostUnregister((void*) c->reg_ptr[i]);
+	for (int i = 0; i < 2; ++i) { if (c->h_stage[i]) cudaFreeHost(c->h_stage[i]); if (c->ev_stage[i]) cudaEventDestroy(c->ev_stage[i]); }
 	for (int i = 0; i < KFB_MAX_SLABS; ++i) if (c->peer_ptrs[i]) cudaIpcCloseMemHandle(c->peer_ptrs[i]);
 	for (int i = 0; i < KFB_MAX_SLABS; ++i)
 		for (int j = 0; j < 4; ++j) if (c->peer_open[i][j]) cudaIpcCloseMemHandle(c->peer_open[i][j]);
@@ -476,7 +484,6 @@ int kfb_destroy(kfb_ctx* c) {
 	cudaFree(c->d_bar); cudaFree(c->d_pose); cudaFree(c->d_frame);
 	if (c->ev_h2d) cudaEventDestroy(c->ev_h2d);
 	cudaFree(c->d_input);
-	if (c->h_stage) cudaFreeHost(c->h_stage);
 	cudaFree(c->d_render);
 	timer_free(c->t_pre); timer_free(c->t_track); timer_free(c->t_int); timer_free(c->t_ray);
 	if (c->ev_window) cudaEventDestroy(c->ev_window);
@@ -568,42 +575,59 @@ int kfb_preprocess(kfb_ctx* c, const uint16_t* depth, uint32_t iw, uint32_t ih) 
 	const size_t bytes = (size_t) iw * ih * sizeof(uint16_t);
 	if ((rc = ensure_input(c, bytes))) return rc;
 	timer_begin(c, c->t_pre, 1u);
-	// Is the caller's buffer already page-locked (ours, torch's pinned pool, or registered before)?
+	// Is the caller's buffer page-locked RIGHT NOW (cudaHostAlloc, torch's pinned pool, cudaHostRegister, or
+	// kfb_register_host_buffer)?  Asked on every call: a cached answer goes stale when the caller frees a buffer and a later
+	// allocation reuses the address.  Pageable memory goes through one of two internal pinned staging buffers.
 	bool pinned = false;
-	for (int i = 0; i < c->n_reg; ++i) if (c->reg_ptr[i] == depth && c->reg_bytes[i] >= bytes) pinned = true;
-	if (!pinned) {
+	{
 		cudaPointerAttributes at;
 		if (cudaPointerGetAttributes(&at, depth) == cudaSuccess && at.type == cudaMemoryTypeHost) pinned = true;
 		else cudaGetLastError();
 	}
-	if (!pinned && c->n_reg < 4) {
-		// benchmark.cpp:103 mallocs ONE frame buffer and reuses it: pin it once, DMA directly afterwards
-		if (cudaHostRegister((void*) depth, bytes, cudaHostRegisterDefault) == cudaSuccess) {
-			c->reg_ptr[c->n_reg] = depth; c->reg_bytes[c->n_reg] = bytes; c->n_reg++;
-			pinned = true;
-		} else cudaGetLastError();
-	}
 	bool on_side = false;
-	cudaStream_t ps = c->stream;
+	cudaStream_t ps = preprocess_stream(c, &on_side);
 	if (pinned) {
-		ps = preprocess_stream(c, &on_side);
 		CK(cudaMemcpyAsync(c->d_input, depth, bytes, cudaMemcpyHostToDevice, ps));
 		CK(cudaEventRecord(c->ev_h2d, ps));
 		c->ev_h2d_pending = true;
 	} else {
-		if (c->stage_bytes < bytes) {
-			if (c->h_stage) CK(cudaFreeHost(c->h_stage));
-			CK(cudaHostAlloc(&c->h_stage, bytes, cudaHostAllocDefault));
-			c->stage_bytes = bytes;
-		}
-		CK(cudaStreamSynchronize(c->stream));  // the staging buffer may still be in flight
-		memcpy(c->h_stage, depth, bytes);
-		CK(cudaMemcpyAsync(c->d_input, c->h_stage, bytes, cudaMemcpyHostToDevice, c->stream));
+		const int sb = c->stage_cur ^= 1;
+		if (c->stage_bytes[sb] < bytes) {
+			if (c->h_stage[sb]) { CK(cudaEventSynchronize(c->ev_stage[sb])); CK(cudaFreeHost(c->h_stage[sb])); c->h_stage[sb] = nullptr; }
+			CK(cudaHostAlloc(&c->h_stage[sb], bytes, cudaHostAllocDefault));
+			c->stage_bytes[sb] = bytes;
+		} else CK(cudaEventSynchronize(c->ev_stage[sb]));   // the copy that last used this staging buffer (two frames ago) has left it
+		memcpy(c->h_stage[sb], depth, bytes);                 // the caller's buffer is free again when this call returns
+		CK(cudaMemcpyAsync(c->d_input, c->h_stage[sb], bytes, cudaMemcpyHostToDevice, ps));
+		CK(cudaEventRecord(c->ev_stage[sb], ps));
 	}
 	c->st.h2d_bytes += bytes;
 	rc = launch_preprocess(c, c->d_input, iw, ratio, ps, on_side);
 	timer_end(c, c->t_pre, 1u);
 	return rc;
+}
+
+int kfb_register_host_buffer(kfb_ctx* c, const void* ptr, size_t bytes) {
+	if (!c || !ptr || !bytes) return set_err(KFB_E_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	for (int i = 0; i < c->n_reg; ++i) if (c->reg_ptr[i] == ptr) return 0;
+	if (c->n_reg >= 8) return set_err(KFB_E_STATE, "too many registered host buffers (8)");
+	CK(cudaHostRegister((void*) ptr, bytes, cudaHostRegisterDefault));
+	c->reg_ptr[c->n_reg++] = ptr;
+	return 0;
+}
+int kfb_unregister_host_buffer(kfb_ctx* c, const void* ptr) {
+	if (!c || !ptr) return set_err(KFB_E_ARG, "null argument");
+	CK(cudaSetDevice(c->device));
+	for (int i = 0; i < c->n_reg; ++i)
+		if (c->reg_ptr[i] == ptr) {
+			CK(cudaStreamSynchronize(c->stream));
+			CK(cudaStreamSynchronize(c->side));
+			CK(cudaHostUnregister((void*) ptr));
+			c->reg_ptr[i] = c->reg_ptr[--c->n_reg];
+			return 0;
+		}
+	return set_err(KFB_E_ARG, "buffer was not registered with this context");
 }
 
 int kfb_preprocess_device(kfb_ctx* c, const uint16_t* d_depth, uint32_t iw, uint32_t ih) {
@@ -841,7 +865,14 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	if (c->brick_off) p.brick.flag = nullptr;
 	p.dmax = (c->dmax_slot >= 0) ? reinterpret_cast<const float*>(c->d_dmax + c->dmax_slot) : nullptr;
 	const uint32_t slot = (uint32_t) (c->integrate_count % NUPD_SLOTS);
-	if (c->integrate_count >= NUPD_SLOTS) CK(cudaMemsetAsync(c->d_nupd + slot, 0, sizeof(unsigned long long), c->stream));
+	if (c->integrate_count >= NUPD_SLOTS) {
+		// a slot is recycled: its count moves into the host-side running total first (rare: once per 4096 integrates)
+		unsigned long long old = 0;
+		CK(cudaStreamSynchronize(c->stream));
+		CK(cudaMemcpy(&old, c->d_nupd + slot, sizeof old, cudaMemcpyDeviceToHost));
+		c->nupd_folded += old;
+		CK(cudaMemsetAsync(c->d_nupd + slot, 0, sizeof(unsigned long long), c->stream));
+	}
 	p.n_upd = c->d_nupd + slot;
 	// pass 1 cuts every warp-column's visited interval into pieces of `zchunk` slices; pass 2 is persistent
 	// short pieces keep every warp's serial chain short (measured: 256^3 best at 16-32, 512^3 at 24-32)
@@ -1135,26 +1166,34 @@ int kfb_dump_volume(kfb_ctx* c, const char* path) {
 	if (!path) return 0;                                           // cpp/kernels.cpp:1010
 	CK(cudaSetDevice(c->device));
 	printf("Dumping the volumetric representation on file: %s\n", path);
-	FILE* f = fopen(path, "wb");
-	if (!f) return set_err(KFB_E_ARG, "Error opening file: %s", path);
+	// a z-slab context writes its slices at their place in the file (tsdf shorts, z order): the ranks of a group fill one dump
+	// (created without truncation there: whichever rank comes first must not wipe what another has written)
+	const int fd = open(path, c->world > 1 ? (O_CREAT | O_WRONLY) : (O_CREAT | O_WRONLY | O_TRUNC), 0644);
+	FILE* f = fd >= 0 ? fdopen(fd, "wb") : nullptr;
+	if (!f) { if (fd >= 0) close(fd); return set_err(KFB_E_ARG, "Error opening file: %s", path); }
+	if (c->world > 1 && fseeko(f, (off_t) ((size_t) c->cfg.volume_res[0] * c->cfg.volume_res[1] * c->z0 * sizeof(short)), SEEK_SET) != 0) {
+		fclose(f);
+		return set_err(KFB_E_ARG, "cannot seek in %s", path);
+	}
 	// stream the slab out plane-group by plane-group: tsdf shorts only, x fastest
 	const size_t plane = (size_t) c->cfg.volume_res[0] * c->cfg.volume_res[1];
 	const uint32_t nz = c->z1 - c->z0;
 	const uint32_t zb = (uint32_t) ((((size_t) 64 << 20) / (plane * sizeof(short))) ? (((size_t) 64 << 20) / (plane * sizeof(short))) : 1);
-	short* d_tmp;
-	CK(cudaMalloc(&d_tmp, plane * zb * sizeof(short)));
+	short* d_tmp = nullptr;
+	cudaError_t e = cudaMalloc(&d_tmp, plane * zb * sizeof(short));
 	std::vector<short> h(plane * zb);
-	for (uint32_t z = 0; z < nz; z += zb) {
+	for (uint32_t z = 0; e == cudaSuccess && z < nz; z += zb) {
 		const uint32_t nzb = (z + zb <= nz) ? zb : nz - z;
 		const size_t n = plane * nzb;
 		k_extract_tsdf<<<148 * 4, 256, 0, c->stream>>>(d_tmp, c->d_vol + plane * z, n);
 		LAUNCHED(c);
-		CK(cudaMemcpyAsync(h.data(), d_tmp, n * sizeof(short), cudaMemcpyDeviceToHost, c->stream));
-		CK(cudaStreamSynchronize(c->stream));
-		fwrite(h.data(), sizeof(short), n, f);
+		e = cudaMemcpyAsync(h.data(), d_tmp, n * sizeof(short), cudaMemcpyDeviceToHost, c->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+		if (e == cudaSuccess) fwrite(h.data(), sizeof(short), n, f);
 	}
 	cudaFree(d_tmp);
 	fclose(f);
+	if (e != cudaSuccess) return set_err(KFB_E_CUDA, "kfb_dump_volume: %s", cudaGetErrorString(e));
 	return 0;
 }
 
@@ -1242,6 +1281,7 @@ int kfb_reset_stats(kfb_ctx* c) {
 	c->t_pre.count = c->t_track.count = c->t_int.count = c->t_ray.count = 0;
 	memset(&c->st, 0, sizeof c->st);
 	c->integrate_count = 0;
+	c->nupd_folded = 0;
 	CK(cudaMemset(c->d_nupd, 0, NUPD_SLOTS * sizeof(unsigned long long)));
 	return 0;
 }
@@ -1253,7 +1293,7 @@ int kfb_get_stats(kfb_ctx* c, kfb_stats* out) {
 	CK(cudaMemcpy(h.data(), c->d_nupd, NUPD_SLOTS * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 	unsigned long long tot = 0;
 	for (auto v : h) tot += v;
-	c->st.voxels_updated_total = tot;
+	c->st.voxels_updated_total = tot + c->nupd_folded;
 	c->st.voxels_updated_last = c->integrate_count ? h[(c->integrate_count - 1) % NUPD_SLOTS] : 0;
 	// totals over all calls since reset_stats (ms_* hold the SUM; divide by the call counts yourself)
 	c->st.ms_preprocess = (float) c->t_pre.total_ms;

@@ -18,6 +18,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <string>
+#include <vector>
+#include <unistd.h>
 
 #include "kfb200.h"
 
@@ -68,8 +71,56 @@ void Kfusion::languageSpecificConstructor() {
 	// benchmark.cpp:153-156 renders the ICP status map every frame: keep the 1-byte status plane
 	cfg.flags = std::getenv("KFB_NO_TRACK_STATUS") ? 0u : KFB_FLAG_TRACK_STATUS;
 	if (std::getenv("KFB_ICP_HOST_SOLVE")) cfg.flags |= KFB_FLAG_ICP_HOST_SOLVE;
+	// z-slab group (BASELINE configs[3], [4]): KFB_WORLD processes run this same binary on the same input, one per GPU;
+	// process KFB_RANK owns slab KFB_RANK of the volume.  The 64-byte CUDA-IPC handles travel through files in KFB_RDV (a
+	// directory all ranks see); after that the library moves every per-frame byte itself over NVLink peer memory and ends
+	// integration() / raycasting() with a barrier over the group (include/kfb200.h, kfb_ipc_import): no MPI, no NCCL.
+	const int world = std::getenv("KFB_WORLD") ? std::atoi(std::getenv("KFB_WORLD")) : 1;
+	const int rank = std::getenv("KFB_RANK") ? std::atoi(std::getenv("KFB_RANK")) : 0;
+	if (world > 1) {
+		if (world > 8 || rank < 0 || rank >= world || !std::getenv("KFB_RDV")) {
+			std::fprintf(stderr, "kfusion-b200: z-slab mode needs 2 <= KFB_WORLD <= 8, 0 <= KFB_RANK < KFB_WORLD and a rendezvous directory KFB_RDV\n");
+			std::exit(1);
+		}
+		const uint32_t layers = (volumeResolution.z + 7) / 8;   // slabs are whole brick layers, as even as they come
+		const uint32_t base = layers / world, extra = layers % world;
+		const uint32_t l0 = rank * base + ((uint32_t) rank < extra ? rank : extra), l1 = l0 + base + ((uint32_t) rank < extra ? 1 : 0);
+		if (base == 0 || computationSize.y % world != 0) {
+			std::fprintf(stderr, "kfusion-b200: cannot cut %u slices / %u image rows over %d ranks\n", volumeResolution.z, computationSize.y, world);
+			std::exit(1);
+		}
+		cfg.slab_z0 = l0 * 8;
+		cfg.slab_z1 = l1 * 8 < volumeResolution.z ? l1 * 8 : volumeResolution.z;
+		cfg.flags |= KFB_FLAG_BRICKS_MERGED;
+		if (!dev) cfg.device = rank;
+	}
 	kfb_ctx* c = NULL;
 	check(kfb_create(&cfg, &c), "kfb_create");
+	if (world > 1) {
+		std::vector<kfb_ipc_handles> all(world);
+		check(kfb_ipc_export(c, &all[rank]), "kfb_ipc_export");
+		const std::string dir = std::getenv("KFB_RDV");
+		{
+			const std::string tmp = dir + "/.handles." + std::to_string(rank) + ".tmp", fin = dir + "/handles." + std::to_string(rank);
+			FILE* f = std::fopen(tmp.c_str(), "wb");
+			if (!f || std::fwrite(&all[rank], sizeof(kfb_ipc_handles), 1, f) != 1) { std::fprintf(stderr, "kfusion-b200: cannot write %s\n", tmp.c_str()); std::exit(1); }
+			std::fclose(f);
+			std::rename(tmp.c_str(), fin.c_str());   // atomic: a peer never reads half a file
+		}
+		for (int r = 0; r < world; ++r) {
+			if (r == rank) continue;
+			const std::string fin = dir + "/handles." + std::to_string(r);
+			FILE* f = NULL;
+			for (int tries = 0; tries < 6000 && !(f = std::fopen(fin.c_str(), "rb")); ++tries) usleep(10000);   // up to 60 s
+			if (!f || std::fread(&all[r], sizeof(kfb_ipc_handles), 1, f) != 1) { std::fprintf(stderr, "kfusion-b200: rank %d never published %s\n", r, fin.c_str()); std::exit(1); }
+			std::fclose(f);
+		}
+		check(kfb_ipc_import(c, rank, world, all.data()), "kfb_ipc_import");
+		const uint32_t rows = computationSize.y / world;
+		check(kfb_set_pixel_rows(c, rank * rows, (rank + 1) * rows), "kfb_set_pixel_rows");
+		check(kfb_peer_barrier(c), "kfb_peer_barrier");   // every rank has mapped every peer before anybody stores into one
+		check(kfb_sync(c), "kfb_sync");
+	}
 	table()[this] = c;
 	_tracked = false;
 	_integrated = false;
@@ -85,7 +136,17 @@ Kfusion::~Kfusion() {
 
 void Kfusion::reset() { check(kfb_reset(ctx_of(this)), "kfb_reset"); }
 
+// the front-ends allocate ONE sensor-frame buffer for the whole run (benchmark.cpp:103): page-lock it the first time it is
+// seen so that every frame is DMA'd straight from it (the library itself never registers a caller's pointer)
+static void pin_frame_buffer(kfb_ctx* c, const ushort* inputDepth, const uint2 inputSize) {
+	static const void* seen = NULL;
+	if (seen == inputDepth) return;
+	seen = inputDepth;
+	kfb_register_host_buffer(c, inputDepth, (size_t) inputSize.x * inputSize.y * sizeof(ushort));   // failure: staged copies
+}
+
 bool Kfusion::preprocessing(const ushort* inputDepth, const uint2 inputSize) {
+	pin_frame_buffer(ctx_of(this), inputDepth, inputSize);
 	check(kfb_preprocess(ctx_of(this), inputDepth, inputSize.x, inputSize.y), "kfb_preprocess");
 	return true;
 }
@@ -123,6 +184,7 @@ void Kfusion::computeFrame(const ushort* inputDepth, const uint2 inputSize, floa
 		float icp_threshold, float mu, const uint frame) {
 	// one C-ABI call: the library enqueues the whole frame before it waits for the pose (kfb_compute_frame)
 	kfb_ctx* c = ctx_of(this);
+	pin_frame_buffer(c, inputDepth, inputSize);
 	float kk[4];
 	k4(k, kk);
 	int tracked = 0, integrated = 0;

@@ -96,3 +96,18 @@ def test_product_never_imports_the_oracle():
                     and "libkfusion_ref" not in src, f
     out = subprocess.check_output(["ldd", b.build_lib()], text=True)
     assert "oracle" not in out
+    # ... nor may any of its build command lines reach into oracle/ (include paths, sources, libraries): record what the
+    # build functions hand to the compilers
+    calls = []
+    real = b.subprocess.check_call
+    b.subprocess.check_call = lambda cmd, **kw: calls.append(list(cmd)) or 0
+    try:
+        b.build_lib(force=True)
+        b.build_variant("probe", ["KFB_PROBE=1"])
+        if os.path.isdir(b.REFERENCE_ROOT):
+            b.build_benchmark(force=True)
+    finally:
+        b.subprocess.check_call = real
+    assert calls
+    for cmd in calls:
+        assert not any("oracle" in str(a) for a in cmd), cmd

@@ -52,3 +52,40 @@ def test_drop_in_benchmark_matches_reference_binary(tmp_path):
     assert (d <= 1).mean() > 0.999
     # and it is fast: the computation column (benchmark.cpp:166) of the tracked frames
     assert a[4:, 7].mean() < b[4:, 7].mean() / 20
+
+
+@pytest.mark.skipif(not os.path.exists(B200_BIN), reason="benchmark binary not built (needs /root/reference at build time)")
+def test_drop_in_benchmark_z_slab_group(tmp_path):
+    """configs[3] from the C++ host: two processes of the SAME drop-in binary (KFB_WORLD / KFB_RANK / KFB_RDV, one GPU each;
+    CUDA-IPC handles through files, everything else over peer memory inside the library) must log the same poses and flags
+    as one process on one GPU, and their slabs must add up to the same volume dump."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n, vres = 12, 128
+    depth, _ = synth.make_sequence(n)
+    raw = str(tmp_path / "seq.raw")
+    synth.write_raw(raw, depth)
+
+    def cmd(tag):
+        return [B200_BIN, "-i", raw, "-s", "4.8", "-p", "0.5,0.5,0.25", "-z", "1000", "-c", "1", "-r", "1", "-t", "1", "-m", "0.1", "-y", "10,5,4",
+                "-l", "1e-5", "-k", "481.2,480,320,240", "-v", str(vres), "-o", str(tmp_path / f"{tag}.log"), "-d", str(tmp_path / f"{tag}.vol")]
+
+    subprocess.run(cmd("one"), check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=600)
+    rdv = tmp_path / "rdv"
+    rdv.mkdir()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, KFB_WORLD="2", KFB_RANK=str(r), KFB_RDV=str(rdv))
+        c = cmd("two")
+        c[c.index("-o") + 1] = str(tmp_path / f"two{r}.log")
+        procs.append(subprocess.Popen(c, env=env, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE))
+    for p in procs:
+        _, err = p.communicate(timeout=600)
+        assert p.returncode == 0, err.decode(errors="replace")[-500:]
+    one, two0, two1 = parse_log(str(tmp_path / "one.log")), parse_log(str(tmp_path / "two0.log")), parse_log(str(tmp_path / "two1.log"))
+    assert one.shape == two0.shape == two1.shape == (n, 14)
+    for two in (two0, two1):
+        assert np.array_equal(one[:, 9:14], two[:, 9:14]), "poses / flags of the z-slab group differ from the single-GPU run"
+    assert np.array_equal(np.fromfile(str(tmp_path / "one.vol"), np.int16), np.fromfile(str(tmp_path / "two.vol"), np.int16))

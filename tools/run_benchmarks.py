@@ -1,4 +1,4 @@
-"""Run kfusion-benchmark-{b200,openmp,cpp} on the same synthetic .raw with the same flags and print
+"""Run kfusion-benchmark-{b200,cuda,openmp,cpp} on the same synthetic .raw with the same flags and print
 frames/s from the `computation` column (benchmark.cpp:166) over frames >= 4, as SURVEY §8d asks.
     python tools/run_benchmarks.py [--volume 256] [--frames 100] [--cpp-frames 20]
 """
@@ -15,6 +15,7 @@ ap.add_argument("--cpp-frames", type=int, default=24, help="frames for the singl
 a = ap.parse_args()
 bins = {"b200": os.path.join(ROOT, "build", "kfusion-benchmark-b200"),
         "openmp": os.path.join(ROOT, "oracle", "_ref", "kfusion-benchmark-openmp"),
+        "cuda": os.path.join(ROOT, "oracle", "_ref", "kfusion-benchmark-cuda"),   # the reference's own CUDA backend, sm_100a
         "cpp": os.path.join(ROOT, "oracle", "_ref", "kfusion-benchmark-cpp")}
 depth, _ = synth.make_sequence(a.frames)
 with tempfile.TemporaryDirectory() as tmp:
