@@ -522,6 +522,9 @@ def sharded_run(args, rank: int, world: int, local_rank: int, torch, dist, volum
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        per_rank = torch.zeros(world, dtype=torch.float64, device=f"cuda:{local_rank}")
+        per_rank[rank] = st["ms_integrate"] / max(1, int(st["frames_integrated"])) * 1e3
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
         err = float(np.abs(s.getPose()[:3, 3] - synth.expected_pose(gt, n - 1)[:3, 3]).max())
         # per-stage breakdown: the same calls with a full sync after each stage (host-visible time, max over ranks)
         stage = np.zeros(4)
@@ -556,7 +559,7 @@ def sharded_run(args, rank: int, world: int, local_rank: int, torch, dist, volum
                 "gpu_launches": int(st["kernel_launches"]) * world,
                 "roofline": {"bound": "hbm", "kernel": "k_integrate_run", "achieved": alg / t_int / 1e9, "peak": peak * world, "unit": "GB/s",
                              "frac": alg / t_int / 1e9 / (peak * world), "traffic": None, "peak_source": peak_src + f" x{world}",
-                             "us_per_launch": t_int * 1e6},
+                             "us_per_launch": t_int * 1e6, "us_per_launch_by_rank": [round(float(v), 1) for v in per_rank]},
                 "stage_ms_per_frame": {"preprocess": float(tstage[0]), "track": float(tstage[1]),
                                        "integrate+barrier": float(tstage[2]), "raycast+band exchange": float(tstage[3]),
                                        "note": "synchronised after every stage, max over ranks"},

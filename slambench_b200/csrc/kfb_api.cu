@@ -6,6 +6,7 @@
 #include "../../include/kfb200.h"
 #include "kfb_kernels.cuh"
 #include "kfb_integrate2.cuh"
+#include "kfb_raycast_bulk.cuh"
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
@@ -123,6 +124,7 @@ struct kfb_ctx {
 	unsigned int* d_tile_ctr;   // two alternating tile counters
 	unsigned int* d_tile_cost;  // KFB_RAY_TILECOST=1: cycles per raycast tile of the last launch (diagnostics)
 	uint64_t ray_launches;
+	bool ray_bulk; unsigned int* d_bulk_stats; int ray_bulk_grid;   // KFB_RAY_BULK=1: the bulk-async (TMA engine) staging experiment
 	uint64_t int_launches;
 	int dmax_slot;              // slot holding the max of the CURRENT floatDepth, -1 = unknown
 	uint64_t preprocess_count;
@@ -346,6 +348,18 @@ static int create_impl(const kfb_config* cfg, kfb_ctx* c) {
 		if (e && atoi(e) > 0 && atoi(e) < per_sm) per_sm = atoi(e);
 		c->ray_grid = sms * per_sm;
 	}
+	{
+		const char* e = getenv("KFB_RAY_BULK");
+		c->ray_bulk = e && atoi(e) > 0 && cfg->volume_res[0] % 8 == 0;
+		if (c->ray_bulk) {
+			int per_sm = 0, sms = 0;
+			CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device));
+			CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_raycast_bulk, RCK_BX * RCK_BY, 0));
+			c->ray_bulk_grid = sms * (per_sm < 1 ? 1 : per_sm);
+			CK(cudaMalloc(&c->d_bulk_stats, 4 * sizeof(unsigned int)));
+			CK(cudaMemsetAsync(c->d_bulk_stats, 0, 4 * sizeof(unsigned int), c->stream));
+		}
+	}
 	CK(cudaMalloc(&c->d_queue_ctr, 4 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_queue_ctr, 0, 4 * sizeof(unsigned int), c->stream));
 	{
@@ -479,6 +493,13 @@ int kfb_destroy(kfb_ctx* c) {
 			fprintf(stderr, "kfb icp profile: %llu iterations; per iteration: last-CTA compute %.2f us, final reduce %.2f us, solve %.2f us, whole iteration (CTA 0) %.2f us\n",
 					h[4], h[0] * 1e-3 / h[4], h[1] * 1e-3 / h[4], h[2] * 1e-3 / h[4], h[3] * 1e-3 / h[4]);
 		cudaFree(c->d_icp_prof);
+	}
+	if (c->d_bulk_stats) {
+		unsigned int h[4];
+		if (cudaMemcpy(h, c->d_bulk_stats, sizeof h, cudaMemcpyDeviceToHost) == cudaSuccess && c->ray_launches)
+			fprintf(stderr, "kfb raycast bulk staging: %llu launches; per launch: %.0f bricks staged, %.0f samples served from shared memory, %u waits timed out in total\n",
+					(unsigned long long) c->ray_launches, (double) h[0] / c->ray_launches, (double) h[1] / c->ray_launches, h[2]);
+		cudaFree(c->d_bulk_stats);
 	}
 	if (c->h_out32) cudaFreeHost(c->h_out32);
 	cudaFree(c->d_bar); cudaFree(c->d_pose); cudaFree(c->d_frame);
@@ -991,7 +1012,8 @@ static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP
 	p.tile_next = c->d_tile_ctr + slot; p.tile_reset = c->d_tile_ctr + (slot ^ 1);
 	// window for the next frame's preprocessing: already open when this raycast directly follows an integrate
 	if (c->overlap_enabled && !c->overlap_ok) CK(cudaEventRecord(c->ev_window, c->stream));
-	k_raycast<<<c->ray_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p);
+	if (c->ray_bulk && c->view_all.n_slabs == 1 && p.n_peer == 0) k_raycast_bulk<<<c->ray_bulk_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p, c->d_bulk_stats);
+	else k_raycast<<<c->ray_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p);
 	LAUNCHED(c);
 	CK(cudaGetLastError());
 	c->overlap_ok = c->overlap_enabled;   // until anything else is enqueued

@@ -182,11 +182,12 @@ struct IntGeom { Mat4 invTrack; float ca[9], tz[3]; };
 // returns false when the device-side gate says "no integrate this frame" (cpp/kernels.cpp:994)
 __device__ __forceinline__ bool int_geom_load(IntGeom& g, const Integrate2Params& q, uint32_t tid) {
 	const DevFrame* d = q.b.dev;
+	const int gate = d ? __ldcg(&d->do_integrate) : 1;   // in flight together with the loads below
 	if (tid < 16) g.invTrack.m[tid] = d ? __ldcg(d->invTrack + tid) : q.b.invTrack.m[tid];
 	else if (tid < 25) g.ca[tid - 16] = d ? __ldcg(d->ca + (tid - 16)) : q.ca[tid - 16];
 	else if (tid < 28) g.tz[tid - 25] = d ? __ldcg(d->tz + (tid - 25)) : q.tz[tid - 25];
 	__syncthreads();
-	return !(d && __ldcg(&d->do_integrate) == 0);
+	return gate != 0;
 }
 
 // Class of the box of voxels [x0, x1] x [y0, y1] x [z0, z1] (inclusive), from linear bounds over the box of their centres
@@ -294,8 +295,11 @@ __device__ __forceinline__ unsigned int item_len(unsigned int m, uint32_t lane, 
 	return len;
 }
 
-__global__ void __launch_bounds__(256, 3) k_integrate_plan2(const __grid_constant__ Integrate2Params q) {
-	__shared__ unsigned int s_mm[8][PLAN_GROUPS], s_ms[8][PLAN_GROUPS];
+#ifndef KFB_PLAN_MINBLOCKS
+#define KFB_PLAN_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(256, KFB_PLAN_MINBLOCKS) k_integrate_plan2(const __grid_constant__ Integrate2Params q) {
+	__shared__ unsigned int s_mm[8][PLAN_GROUPS], s_ms[8][PLAN_GROUPS], s_mf[8][PLAN_GROUPS];
 	__shared__ IntGeom geom;
 	const IntegrateParams& p = q.b;
 	const uint32_t lane = threadIdx.x;
@@ -317,11 +321,12 @@ __global__ void __launch_bounds__(256, 3) k_integrate_plan2(const __grid_constan
 	for (uint32_t pass0 = bz0; pass0 < bz1; pass0 += 32 * PLAN_GROUPS) {
 		unsigned int* mm = s_mm[threadIdx.y];   // per group: MIXED layers / first layers of the MIXED items (rolled loops: small code)
 		unsigned int* ms = s_ms[threadIdx.y];
-		unsigned int n_half = 0;
-		// pass 1: classes, FREE items, and the number of MIXED items of the column
+		unsigned int* mf = s_mf[threadIdx.y];   // per group: FREE layers
+		unsigned int n_half = 0, n_free = 0;
+		// pass 1: classes, and the number of items of the column
 #pragma unroll 1
 		for (int g = 0; g < PLAN_GROUPS; ++g) {
-			if (lane == 0) { mm[g] = 0u; ms[g] = 0u; }
+			if (lane == 0) { mm[g] = 0u; ms[g] = 0u; mf[g] = 0u; }
 			if (pass0 + 32 * g >= bz1) continue;   // warp-uniform
 			const uint32_t bz = pass0 + 32 * g + lane;
 			int c = CLS_SKIP;
@@ -330,25 +335,36 @@ __global__ void __launch_bounds__(256, 3) k_integrate_plan2(const __grid_constan
 				q.cls[((size_t) (bz - bz0) * q.bny + by) * q.bnx + bx] = (unsigned char) c;
 			}
 			const unsigned int m_mixed = __ballot_sync(0xffffffffu, c >= CLS_MIXED_IN), m_starts = item_starts(m_mixed, lane, INT_MIXED_CAP);
-			if (lane == 0) { mm[g] = m_mixed; ms[g] = m_starts; }
+			const unsigned int m_free = __ballot_sync(0xffffffffu, c == CLS_FREE);
+			if (lane == 0) { mm[g] = m_mixed; ms[g] = m_starts; mf[g] = m_free; }
 			n_half += __popc(m_starts);
-			// FREE items of this group go out at once (they need no order)
-			const unsigned int mf = __ballot_sync(0xffffffffu, c == CLS_FREE);
-			if (mf) {
-				const unsigned int fs = item_starts(mf, lane, 2u);
-				unsigned int base_f = 0;
-				if (lane == 0) base_f = atomicAdd(q.ctr + 1, (unsigned int) __popc(fs));
-				base_f = __shfl_sync(0xffffffffu, base_f, 0);
-				if ((fs >> lane) & 1u) q.q_free[base_f + __popc(fs & lt)] = make_uint2(bx | (by << 12), bz | (item_len(mf, lane, 2u) << 16));
-			}
+			n_free += __popc(item_starts(m_free, lane, 2u));
 		}
-		if (n_half == 0) continue;
-		// the column's MIXED items take one contiguous range, [half 0's items in z order][half 1's items in z order],
-		// and one REPLAY job per half
-		unsigned int base_m = 0, base_r = 0;
-		if (lane == 0) { base_m = atomicAdd(q.ctr + 0, n_half * halves); base_r = atomicAdd(q.ctr + 3, halves); }
+		if (n_half == 0 && n_free == 0) continue;
+		// One round trip to the queue counters per column (they are hot: 4096 warps): the column's MIXED items take one
+		// contiguous range, [half 0's items in z order][half 1's items in z order], plus one REPLAY job per half; its FREE
+		// items another range (they need no order).
+		unsigned int base_m = 0, base_r = 0, base_f = 0;
+		if (lane == 0) {
+			if (n_half) { base_m = atomicAdd(q.ctr + 0, n_half * halves); base_r = atomicAdd(q.ctr + 3, halves); }
+			if (n_free) base_f = atomicAdd(q.ctr + 1, n_free);
+		}
 		base_m = __shfl_sync(0xffffffffu, base_m, 0);
 		base_r = __shfl_sync(0xffffffffu, base_r, 0);
+		base_f = __shfl_sync(0xffffffffu, base_f, 0);
+		__syncwarp();
+		if (n_free) {
+			unsigned int at_f = base_f;
+#pragma unroll 1
+			for (int g = 0; g < PLAN_GROUPS; ++g) {
+				const unsigned int m_free = mf[g];
+				if (m_free == 0u) continue;
+				const unsigned int fs = item_starts(m_free, lane, 2u);
+				if ((fs >> lane) & 1u) q.q_free[at_f + __popc(fs & lt)] = make_uint2(bx | (by << 12), (pass0 + 32 * g + lane) | (item_len(m_free, lane, 2u) << 16));
+				at_f += __popc(fs);
+			}
+		}
+		if (n_half == 0) { __syncwarp(); continue; }
 		if (lane < halves) q.q_replay[base_r + lane] = make_uint4(bx | (by << 12) | (lane << 24), base_m + lane * n_half, n_half, 0u);
 		unsigned int at_m = base_m;
 		__syncwarp();
@@ -469,25 +485,42 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 	const size_t plane = (size_t) p.sx * p.sy;
 	const unsigned int n_mixed = __ldcg(q.ctr + 0), n_free = __ldcg(q.ctr + 1), n_replay = __ldcg(q.ctr + 3);
 	const unsigned int n_items = n_replay + n_mixed + n_free;
-	// claim order: all REPLAY jobs (long serial chains: started first), then the FREE items (pure memory streaming: the warps
-	// that got no job stream while the jobs run, so no MIXED item ever waits for its checkpoint), then the MIXED items
+	// claim order: all REPLAY jobs (long serial chains: started first), then MIXED and FREE items interleaved k : 1 — the FREE
+	// items are pure memory streaming, the MIXED ones latency / issue bound: together on an SM they overlap — then what is
+	// left of either kind.  (A MIXED item claimed while its REPLAY job still runs waits on the job's flag.)
+#ifndef INT_INTERLEAVE
+#define INT_INTERLEAVE 1
+#endif
+	const unsigned int k_mix = n_free ? max(1u, n_mixed / n_free) : 1u;
+	const unsigned int n_groups = min(n_free, n_mixed / k_mix);
 	unsigned int updated = 0;
 
-	// one claim ahead: the atomic's round trip to the single hot counter (~1-2 us with 4700 warps on it) hides behind the
-	// current item; items are small, so the item a warp holds in reserve costs the tail little
-	unsigned int nxt = 0;
-	if (lane == 0) nxt = atomicAdd(q.ctr + 2, 1u);
 	for (;;) {
-		unsigned int it = __shfl_sync(0xffffffffu, nxt, 0);
+		unsigned int it = 0;
+		if (lane == 0) it = atomicAdd(q.ctr + 2, 1u);   // (claiming one item ahead was measured: 83 -> 92 us, the reserve item delays the tail)
+		it = __shfl_sync(0xffffffffu, it, 0);
 		if (it >= n_items) break;
-		if (lane == 0) nxt = atomicAdd(q.ctr + 2, 1u);
 		if (it < n_replay) {
 			integrate_replay_job(q, geom, __ldcg(q.q_replay + it), lane);
 			continue;
 		}
 		it -= n_replay;
-		const bool is_free = it < n_free;
-		const unsigned int idx = is_free ? it : it - n_free;
+		bool is_free;
+		unsigned int idx;
+#if INT_INTERLEAVE
+		if (it < n_groups * (k_mix + 1)) {
+			const unsigned int grp = it / (k_mix + 1), pos = it - grp * (k_mix + 1);
+			is_free = pos == k_mix;
+			idx = is_free ? grp : grp * k_mix + pos;
+		} else {
+			const unsigned int rest = it - n_groups * (k_mix + 1), mixed_left = n_mixed - n_groups * k_mix;
+			is_free = rest >= mixed_left;
+			idx = is_free ? n_groups + (rest - mixed_left) : n_groups * k_mix + rest;
+		}
+#else
+		is_free = it < n_free;
+		idx = is_free ? it : it - n_free;
+#endif
 		if (is_free) {
 			// ---------------- FREE item: 1 or 2 bricks (bx, by, bz ..): per instruction 2 slices x 8 rows x 2 half-rows of 4 voxels
 			const uint2 item = __ldcg(q.q_free + idx);

@@ -491,15 +491,94 @@ __device__ __forceinline__ unsigned int ld_relaxed_u32(const unsigned int* p) {
 	return v;
 }
 
-// one thread: updatePoseKernel (:759-775) on the device copy of the pose
-__device__ __noinline__ int icp_solve(float* pose_dev, const float* red32, float icp_threshold) {
-	float pose[16];
+// hm_solve6_chol (kfb_hostmath.h) spread over lanes 0..5 of a warp: lane i owns row i of the Cholesky factor and column i of
+// its inverse, so the ~250 dependent fp64 operations of the one-thread version become chains of ~40.  Every entry is
+// computed with the same operations in the same order as there (bit-identical x); only the certificate's trace(C^-1) is
+// summed column-wise.  All 32 lanes must call; returns 0 (uniformly) when the certificate fails.
+__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+#define KFB_UP(r, c) (6 + 6 * (r) - (r) * ((r) - 1) / 2 + ((c) - (r)))   // vals27 index of C[r][c], c >= r (commons.h:385-392)
+__device__ __forceinline__ int icp_solve6_chol_warp(double* x6, const float* __restrict__ vals27, int lane) {
+	const int i = lane < 6 ? lane : 5;    // lanes >= 6 mirror lane 5 (their results are never read)
+	double Lr[6];
 #pragma unroll
-	for (int i = 0; i < 16; ++i) pose[i] = pose_dev[i];
-	const int conv = hm_update_pose_fast(pose, red32, icp_threshold);
+	for (int k = 0; k < 6; ++k) Lr[k] = (k <= i) ? (double) vals27[KFB_UP(k, i)] : 0.0;
+	double diag = 0;
 #pragma unroll
-	for (int i = 0; i < 16; ++i) pose_dev[i] = pose[i];
-	return conv;
+	for (int k = 0; k < 6; ++k) if (k == i) diag = Lr[k];
+	double trC = 0;
+#pragma unroll
+	for (int r = 0; r < 6; ++r) trC += shfl_d(diag, r);
+	double invd[6];
+	bool ok = true;
+#pragma unroll
+	for (int j = 0; j < 6; ++j) {
+		double s = Lr[j];
+#pragma unroll
+		for (int k = 0; k < j; ++k) s -= Lr[k] * shfl_d(Lr[k], j);
+		const double sj = shfl_d(s, j);
+		if (!(sj > 0)) ok = false;
+		const double inv = rsqrt(sj), d = sj * inv;
+		invd[j] = inv;
+		Lr[j] = (i == j) ? d : s * inv;   // rows i < j: never read again
+	}
+	if (!ok) return 0;
+	// all of L to every lane, then lane j inverts column j:  M(j,j) = 1 / L(j,j);  M(i,j) = -(sum_{k=j}^{i-1} L(i,k) M(k,j)) / L(i,i)
+	double Lf[6][6];
+#pragma unroll
+	for (int r = 1; r < 6; ++r)
+#pragma unroll
+		for (int k = 0; k < r; ++k) Lf[r][k] = shfl_d(Lr[k], r);
+	double Mc[6];
+	double sq = 0;
+#pragma unroll
+	for (int r = 0; r < 6; ++r) {
+		double t = 0;
+#pragma unroll
+		for (int k = 0; k < r; ++k) if (k >= i) t -= Lf[r][k] * Mc[k];
+		Mc[r] = (r == i) ? invd[r] : ((r > i) ? t * invd[r] : 0.0);
+		sq += Mc[r] * Mc[r];
+	}
+	double trInv = 0;
+#pragma unroll
+	for (int r = 0; r < 6; ++r) trInv += shfl_d(sq, r);
+	if (!(trC * trInv < 0.99e6)) return 0;
+	const double bi = (double) vals27[i];
+	double y[6];
+#pragma unroll
+	for (int r = 0; r < 6; ++r) {
+		const double term = Mc[r] * bi;   // M(r, i) b_i, zero for i > r
+		double t = 0;
+#pragma unroll
+		for (int j = 0; j <= r; ++j) t += shfl_d(term, j);
+		y[r] = t;
+	}
+	double xi = 0;
+#pragma unroll
+	for (int r = 0; r < 6; ++r) if (r >= i) xi += Mc[r] * y[r];
+#pragma unroll
+	for (int j = 0; j < 6; ++j) x6[j] = shfl_d(xi, j);
+	return 1;
+}
+
+// warp 0 of the last CTA: updatePoseKernel (:759-775) on the device copy of the pose
+__device__ __noinline__ int icp_solve(float* pose_dev, const float* pose_cur, const float* red32, float icp_threshold, int lane) {
+	double x[6];
+	const int fast = icp_solve6_chol_warp(x, red32 + 1, lane);
+	int conv = 0;
+	if (lane == 0) {
+		if (!fast) hm_solve6(x, red32 + 1);   // not positive definite / possibly ill-conditioned: the pseudo-inverse
+		float pose[16], d[16];
+#pragma unroll
+		for (int i = 0; i < 16; ++i) pose[i] = pose_cur[i];   // this CTA's shared-memory copy of the current pose: no L2 round trip
+		hm_se3_exp(d, x);
+		hm_matmul4(pose, d, pose);
+#pragma unroll
+		for (int i = 0; i < 16; ++i) pose_dev[i] = pose[i];
+		double n = 0;
+		for (int i = 0; i < 6; ++i) n += x[i] * x[i];
+		conv = sqrt(n) < (double) icp_threshold;
+	}
+	return __shfl_sync(0xffffffffu, conv, 0);
 }
 
 __device__ __forceinline__ unsigned long long gtime_ns() {
@@ -537,6 +616,9 @@ __device__ __noinline__ void icp_tail(const IcpParams& p) {
 #ifndef ICP_THREADS
 #define ICP_THREADS 512   // one CTA per SM: half the partial rows for the last CTA to sum (measured 12.0 -> 11.3 us / iteration)
 #endif
+#ifndef ICP_PX
+#define ICP_PX 2   // measured: 4 pixels per round is slower (5.3 vs 4.8 us of per-iteration compute: registers, longer reduction tail)
+#endif
 #define ICP_NW (ICP_THREADS / 32)          // warps per CTA
 #define ICP_VPW (32 / ICP_NW)              // reduction outputs summed by each warp
 #define ICP_SMEM_BYTES (32 * ICP_THREADS * sizeof(float))
@@ -562,10 +644,13 @@ __global__ void __launch_bounds__(ICP_THREADS, 512 / ICP_THREADS) k_icp(const __
 			const Mat4 T = Tsh;
 			TrackAcc acc;
 			acc.clear();
-			for (uint32_t i = blockIdx.x * ICP_THREADS + threadIdx.x; i < npx; i += 2 * gridDim.x * ICP_THREADS) {
-				const uint32_t pix[2] = { i, i + gridDim.x * ICP_THREADS };
-				const bool on[2] = { true, pix[1] < npx };
-				track_pixels<2>(acc, p.inV[level], p.inN[level], p.refV, p.refN, w, p.rw, p.rh, pix, on, T, V, p.dist_threshold,
+			// ICP_PX pixels per thread and round, all their loads in flight together
+			for (uint32_t i = blockIdx.x * ICP_THREADS + threadIdx.x; i < npx; i += ICP_PX * gridDim.x * ICP_THREADS) {
+				uint32_t pix[ICP_PX];
+				bool on[ICP_PX];
+#pragma unroll
+				for (int u = 0; u < ICP_PX; ++u) { pix[u] = i + u * gridDim.x * ICP_THREADS; on[u] = pix[u] < npx; }
+				track_pixels<ICP_PX>(acc, p.inV[level], p.inN[level], p.refV, p.refN, w, p.rw, p.rh, pix, on, T, V, p.dist_threshold,
 						p.normal_threshold, p.status);
 			}
 			// thread -> CTA through shared memory, fp64, fixed order: value i of thread t sits at xs[i][t]; warp w
@@ -624,13 +709,9 @@ __global__ void __launch_bounds__(ICP_THREADS, 512 / ICP_THREADS) k_icp(const __
 					red32[lane] = r;
 					p.out32[lane] = r;            // device copy; mirrored to the host once, at the end
 					__syncwarp();
+					if (lane == 0 && p.prof) tp2 = gtime_ns();
+					const int c = icp_solve(p.pose_dev, Tsh.m, red32, p.icp_threshold, lane);   // the whole warp: lane-parallel Cholesky
 					if (lane == 0) {
-						if (p.prof) tp2 = gtime_ns();
-						if (step == 1) {
-#pragma unroll
-							for (int i = 0; i < 16; ++i) p.pose_dev[i] = p.pose0.m[i];
-						}
-						const int c = icp_solve(p.pose_dev, red32, p.icp_threshold);
 						if (p.prof) {   // last CTA: [0] own compute, [1] final reduce, [2] solve (ns, summed over iterations)
 							tp3 = gtime_ns();
 							atomicAdd(p.prof + 0, tp1 - tp0); atomicAdd(p.prof + 1, tp2 - tp1); atomicAdd(p.prof + 2, tp3 - tp2);

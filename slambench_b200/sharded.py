@@ -56,10 +56,11 @@ def slab_bounds(n_z: int, world: int, weights=None, align: int = 1) -> list[tupl
         raise ValueError("weights must be one non-negative number per slice")
     w = w + w.sum() * 0.02 / n_z + 1e-12          # a floor: empty regions still cost the raycaster's peer reads
 
-    # cost of a slab [a, b): its visited voxels (~100 warp-instructions per 32-voxel slice row) plus the replay of
-    # the reference's additions from z = 0 up to the slab for every column it visits (~3.4 per step)
+    # cost of a slab [a, b): the work of its slices (frustum_slice_weights already weighs per-voxel bricks against
+    # free-space ones) plus, for slabs that hold per-voxel work, the replay of the reference's additions from z = 0 up to
+    # the slab (once per column half: a small term since round 2)
     def cost(a, b):
-        return 100.0 * w[a:b].sum() + 3.4 * a * w[a:b].max()
+        return w[a:b].sum() + 0.002 * a * w[a:b].max()
 
     # minimise the largest slab cost: bisection on the bound, greedy cuts from the far end
     cand = list(range(0, n_z + 1, align))
@@ -101,10 +102,11 @@ def slab_bounds(n_z: int, world: int, weights=None, align: int = 1) -> list[tupl
 
 
 def frustum_slice_weights(n_z: int, volume_dim: float, pose, k, image_wh, far: float = 4.0, mu: float = 0.1):
-    """Expected integrate work per z-slice for a camera at `pose`: the area of the slice that projects into the
-    image at a depth the sensor can report (the voxels integrate visits, cpp/kernels.cpp:647-661).  Used once, at
-    set-up, to place the slab boundaries; the partition stays valid while the camera moves little compared with
-    the volume (it is only a load-balance heuristic: any partition gives the same voxels)."""
+    """Expected integrate work per z-slice for a camera at `pose` that sees surfaces around depth `far`: the area of the
+    slice that projects into the image, weighted by what integrate does there (cpp/kernels.cpp:647-661 as k_integrate_run2
+    executes it): free space in front of the surface is a streaming update (weight 1), the band around the surface is
+    decided voxel by voxel (weight 3: roughly the measured cost ratio of the two paths), behind it nothing happens (0).  Used once, at
+    set-up, to place the slab boundaries; it is only a load-balance heuristic: any partition gives the same voxels."""
     pose = np.asarray(pose, np.float64).reshape(4, 4)
     fx, fy, cx, cy = [float(v) for v in k]
     w, h = image_wh
@@ -112,13 +114,15 @@ def frustum_slice_weights(n_z: int, volume_dim: float, pose, k, image_wh, far: f
     g = (np.arange(n) + 0.5) / n * volume_dim
     X, Y = np.meshgrid(g, g)
     Rinv, t = pose[:3, :3].T, pose[:3, 3]
+    band = 2.5 * mu                                            # mu plus the slack of brick-granular decisions, generously
     out = np.zeros(n_z)
     for z in range(n_z):
         P = np.stack([X - t[0], Y - t[1], np.full_like(X, (z + 0.5) / n_z * volume_dim - t[2])], -1) @ Rinv.T
         d = P[..., 2]
         with np.errstate(divide="ignore", invalid="ignore"):
             u, v = fx * P[..., 0] / d + cx, fy * P[..., 1] / d + cy
-        out[z] = np.count_nonzero((d > 1e-4) & (d < far + mu) & (u >= 0) & (u <= w - 1) & (v >= 0) & (v <= h - 1))
+        inside = (d > 1e-4) & (u >= 0) & (u <= w - 1) & (v >= 0) & (v <= h - 1)
+        out[z] = np.count_nonzero(inside & (d < far - band)) + 3.0 * np.count_nonzero(inside & (np.abs(d - far) <= band))
     return out
 
 

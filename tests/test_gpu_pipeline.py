@@ -289,6 +289,24 @@ def test_odd_configurations(port, seq16, res, dim, csize, pyr, pose_tol):
     assert ((a[4][..., 0] != -2) == (nrm_c[..., 0] != -2)).mean() > 0.99
 
 
+@pytest.mark.parametrize("vres", [128, 200])
+def test_raycast_bulk_staging_is_exact(seq16, vres, monkeypatch):
+    """The bulk-async staging experiment (KFB_RAY_BULK=1: flagged bricks copied into shared memory by cp.async.bulk + mbarrier,
+    taps read from there) must produce the same maps, poses and volume as the __ldg gather path, bit for bit
+    (200^3: bricks cut by the volume's edge)."""
+    depth, _ = seq16
+    res = []
+    for bulk in ("0", "1"):
+        monkeypatch.setenv("KFB_RAY_BULK", bulk)
+        with kf.Kfusion((640, 480), vres, 4.8, T0, (10, 5, 4)) as g:
+            for f in range(10):
+                g.computeFrame(depth[f], None, K, 1, 1, 1e-5, 0.1, f)
+            res.append((g.getPose().copy(), g.read(kf.BUF_VERTEX), g.read(kf.BUF_NORMAL), g.read(kf.BUF_VOLUME)))
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a, b.view(np.uint32) if b.dtype == np.float32 else b)
+    assert (res[1][2][..., 0] != -2).mean() > 0.5, "nothing was hit: the staged path was not exercised"
+
+
 @pytest.mark.parametrize("rates", [(1, 1), (2, 3)])
 def test_compute_frame_entry_point(seq16, rates):
     """kfb_compute_frame == preprocessing + tracking + integration + raycasting (cpp/kernels.cpp:1048-1055), bit for bit:
