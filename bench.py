@@ -73,13 +73,17 @@ def peaks():
 
 
 def traffic_bytes(args):
-    """DRAM bytes per integrate launch from the committed ncu capture (profiles/integrate_traffic.json), or null."""
+    """(DRAM bytes per integrate launch, note) from the committed ncu capture (profiles/integrate_traffic.json), or (None, why).
+    It is a CAPTURE, not a live measurement: the note names its file and the N_upd it was taken at."""
     if args.traffic_bytes is not None:
-        return args.traffic_bytes
+        return args.traffic_bytes, "--traffic-bytes"
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "integrate_traffic.json"))).get(str(args.volume))
-    except Exception:
-        return None
+        e = json.load(open(os.path.join(ROOT, "profiles", "integrate_traffic.json"))).get(str(args.volume))
+        if e is None:
+            return None, "no ncu capture committed for this volume"
+        return e["bytes"], f"ncu capture {e['source']} at N_upd = {e['n_upd']} (algorithmic bytes of that launch: {e['algorithmic_bytes']})"
+    except Exception as ex:  # noqa: BLE001
+        return None, f"profiles/integrate_traffic.json unreadable: {ex}"
 
 
 # ---------------------------------------------------------------------------------- clocks
@@ -368,8 +372,8 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
         achieved = alg_bytes / t_int_s / 1e9 if t_int_s > 0 else 0.0
         full_sweep_bytes = 8.0 * args.volume ** 3 + 4.0 * P_PIX
         roof = {
-            "bound": "hbm", "kernel": "k_integrate_plan + k_integrate_run", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic_bytes(args), "peak_source": peak_src,
+            "bound": "hbm", "kernel": "k_integrate_plan2 + k_integrate_free_runs + k_integrate_run2", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic_bytes(args)[0], "traffic_source": traffic_bytes(args)[1], "peak_source": peak_src,
             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": t_int_s * 1e6,
             "n_upd_per_launch": st["voxels_updated_total"] / n_int,
             "full_sweep_gbs": full_sweep_bytes / t_int_s / 1e9 if t_int_s > 0 else 0.0,
@@ -424,7 +428,7 @@ def b200_arm(args, rank: int, world: int, local_rank: int):
             if rank == 0:
                 sh[str(vol)] = {"value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "scaling": "strong",
                                 "steps": r["steps"], "workload": r["config"]["workload"], "parallelism": r["config"]["parallelism"],
-                                "slabs": r["config"]["slabs"], "tracked_frames": r["config"]["tracked_frames"],
+                                "slabs": r["config"]["slabs"], "slab_calibration": r["config"]["slab_calibration"], "tracked_frames": r["config"]["tracked_frames"],
                                 "final_pose_err_m": r["config"]["final_pose_err_m"], "roofline": r["roofline"],
                                 "stage_ms_per_frame": r["stage_ms_per_frame"]}
     if rank == 0:
@@ -484,9 +488,41 @@ def sharded_run(args, rank: int, world: int, local_rank: int, torch, dist, volum
         depth_np, gt = render_sequence_distributed(n + n_diag, rank, world, torch, dist, f"cuda:{local_rank}")
     host = torch.from_numpy(depth_np).pin_memory()
     depth_np = host.numpy()
+    slabs, calib = None, []
+    if not args.even_slabs and not args.no_calibration:
+        # Calibration (set-up, untimed): a few short runs of the first frames; after each, the integrate time of every slab is
+        # measured, the per-slice cost density refitted to it (sharded.refit_density) and the boundaries moved so that the
+        # slabs cost the same.  The cost of a slice depends on what the camera sees, which no a-priori model knows.
+        from slambench_b200 import kfusion as kf_
+
+        n_cal = min(n, 12)
+        dens = sharded.frustum_slice_weights(volume, VOLUME_DIM, kf_.identity_pose(T0), K, (W_IMG, H_IMG), far=float(depth_np[0].max()) / 1000.0)
+        dens = dens + dens.sum() * 0.02 / volume
+        slabs = sharded.equalise_slabs(dens, world)
+        for it in range(3):
+            with sharded.ShardedKfusion((W_IMG, H_IMG), volume, VOLUME_DIM, T0, PYRAMID, rank=rank, world=world, device=local_rank,
+                                        icp_mode=args.icp_mode, slabs=slabs) as s:
+                g = s.local
+                for f in range(n_cal):
+                    if f == 4:
+                        s.synchroniseDevices()
+                        g.enable_timing(4)
+                        g.reset_stats()
+                    s.preprocessing(depth_np[f]); s.tracking(K, ICP_THRESHOLD, 1, f); s.integration(K, 1, MU, f); s.raycasting(K, MU, f)
+                s.synchroniseDevices()
+                st_c = g.stats()
+                tms = torch.zeros(world, dtype=torch.float64, device=f"cuda:{local_rank}")
+                tms[rank] = st_c["ms_integrate"] / max(1, int(st_c["frames_integrated"]))
+                dist.all_reduce(tms)
+            times = [float(v) for v in tms]
+            calib.append({"slabs": [list(z) for z in slabs], "integrate_us": [round(1e3 * t, 1) for t in times]})
+            if max(times) < 1.08 * (sum(times) / world):
+                break
+            dens = sharded.refit_density(dens, slabs, times)
+            slabs = sharded.equalise_slabs(dens, world)
     with sharded.ShardedKfusion((W_IMG, H_IMG), volume, VOLUME_DIM, T0, PYRAMID, rank=rank, world=world, device=local_rank,
                                 icp_mode=args.icp_mode, balance_k=None if args.even_slabs else K,
-                                balance_far=float(depth_np[0].max()) / 1000.0) as s:
+                                balance_far=float(depth_np[0].max()) / 1000.0, slabs=slabs) as s:
         g = s.local
         stream = g.torch_stream(torch)
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -552,7 +588,7 @@ def sharded_run(args, rank: int, world: int, local_rank: int, torch, dist, volum
                 "config": {"workload": workload_name(volume), "volume": volume, "frames": n,
                            "parallelism": f"z-slab x{world}: integrate local, raycast via NVLink peer slabs, map bands + brick flags stored into the "
                                           f"peers, peer-memory barriers ({s.transport} transport), ICP {args.icp_mode}",
-                           "slabs": [list(z) for z in s.slabs],
+                           "slabs": [list(z) for z in s.slabs], "slab_calibration": calib,
                            "tracked_frames": int(tracked), "final_pose_err_m": err},
                 "e2e": {"value": steps / (ms_all * 1e-3), "unit": UNIT, "h2d_bytes_per_step": W_IMG * H_IMG * 2,
                         "d2h_bytes_per_step": st["d2h_bytes"] / steps},
@@ -587,6 +623,7 @@ def main():
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the extra z-slab (configs[3]/[4]) runs")
     ap.add_argument("--sharded-steps", type=int, default=20, help="timed frames of the z-slab runs added to the N > 1 line")
     ap.add_argument("--even-slabs", action="store_true", help="sharded mode: equal z-slabs instead of the load-aware boundaries")
+    ap.add_argument("--no-calibration", action="store_true", help="sharded mode: keep the a-priori slab boundaries (no measured rebalancing pass)")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes/launch of k_integrate from the ncu capture in profiles/")
     args = ap.parse_args()
     if args.warmup < 3:

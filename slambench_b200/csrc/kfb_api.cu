@@ -412,7 +412,7 @@ static int create_impl(const kfb_config* cfg, kfb_ctx* c) {
 			c->ckpt_cap = (unsigned int) cap;
 			CK(cudaMalloc(&c->d_ckpt, cap * 96 * sizeof(unsigned long long)));
 		}
-		CK(cudaMalloc(&c->d_qfree, (size_t) bnx * bny * ((bnz + 1) / 2 + 1) * sizeof(uint2)));
+		CK(cudaMalloc(&c->d_qfree, (size_t) bnx * bny * bnz * sizeof(uint2)));   // worst case: every FREE brick an item of its own
 		CK(cudaMalloc(&c->d_qreplay, (size_t) bnx * bny * 2 * ((bnz + 255) / 256) * sizeof(uint4)));
 		CK(cudaMalloc(&c->d_ready, (size_t) bnx * bny * 2 * ((bnz + 255) / 256) * sizeof(unsigned int)));
 		CK(cudaMemsetAsync(c->d_ready, 0, (size_t) bnx * bny * 2 * ((bnz + 255) / 256) * sizeof(unsigned int), c->stream));
@@ -954,6 +954,8 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 		dim3 block(32, 8), grid(q.bnx, (q.bny + 7) / 8);
 		k_integrate_plan2<<<grid, block, 0, c->stream>>>(q);
 		LAUNCHED(c);
+		k_integrate_free_runs<<<dim3(q.bny, (((p.z_end + 7) >> 3) - (p.z_begin >> 3) + 7) / 8), dim3(32, 8), 0, c->stream>>>(q);
+		LAUNCHED(c);
 		k_integrate_run2<<<c->int_grid2, 256, 0, c->stream>>>(q);
 		LAUNCHED(c);
 	}
@@ -1012,7 +1014,7 @@ static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP
 	p.tile_next = c->d_tile_ctr + slot; p.tile_reset = c->d_tile_ctr + (slot ^ 1);
 	// window for the next frame's preprocessing: already open when this raycast directly follows an integrate
 	if (c->overlap_enabled && !c->overlap_ok) CK(cudaEventRecord(c->ev_window, c->stream));
-	if (c->ray_bulk && c->view_all.n_slabs == 1 && p.n_peer == 0) k_raycast_bulk<<<c->ray_bulk_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p, c->d_bulk_stats);
+	if (c->ray_bulk) k_raycast_bulk<<<c->ray_bulk_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p, c->d_bulk_stats);
 	else k_raycast<<<c->ray_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p);
 	LAUNCHED(c);
 	CK(cudaGetLastError());

@@ -270,7 +270,7 @@ __device__ __noinline__ int classify_box(const Integrate2Params& q, const IntGeo
 //          per-voxel bricks in one 8x4-voxel half of a brick column.  `cells`: 2 bits per step of 4 slices — the class of
 //          that 8 x 4 x 4 cell of voxels, classified like a brick but on a quarter of its volume: inside a brick that is
 //          MIXED as a whole, about 40 % of the cells are still all-SKIP or all-FREE.
-//   FREE   { bx | by << 12,  bz_first | n_bricks << 16 }: 1 or 2 bricks of one column.
+//   FREE   { bx_first | by << 12 | log2(len) << 24,  bz }: 2^k (<= 16) FREE bricks in a row ALONG X (k_integrate_free_runs).
 //   REPLAY { bx | by << 12 | half << 24, first MIXED item, #items, 0 }: one per column half that has MIXED items (they
 //          are contiguous and in z order): the reference's additions (cpp/kernels.cpp:646-647) replayed ONCE from z = 0,
 //          the running values stored as a CHECKPOINT at the first slice of every item.
@@ -299,7 +299,7 @@ __device__ __forceinline__ unsigned int item_len(unsigned int m, uint32_t lane, 
 #define KFB_PLAN_MINBLOCKS 3
 #endif
 __global__ void __launch_bounds__(256, KFB_PLAN_MINBLOCKS) k_integrate_plan2(const __grid_constant__ Integrate2Params q) {
-	__shared__ unsigned int s_mm[8][PLAN_GROUPS], s_ms[8][PLAN_GROUPS], s_mf[8][PLAN_GROUPS];
+	__shared__ unsigned int s_mm[8][PLAN_GROUPS], s_ms[8][PLAN_GROUPS];
 	__shared__ IntGeom geom;
 	const IntegrateParams& p = q.b;
 	const uint32_t lane = threadIdx.x;
@@ -321,12 +321,11 @@ __global__ void __launch_bounds__(256, KFB_PLAN_MINBLOCKS) k_integrate_plan2(con
 	for (uint32_t pass0 = bz0; pass0 < bz1; pass0 += 32 * PLAN_GROUPS) {
 		unsigned int* mm = s_mm[threadIdx.y];   // per group: MIXED layers / first layers of the MIXED items (rolled loops: small code)
 		unsigned int* ms = s_ms[threadIdx.y];
-		unsigned int* mf = s_mf[threadIdx.y];   // per group: FREE layers
-		unsigned int n_half = 0, n_free = 0;
+		unsigned int n_half = 0;
 		// pass 1: classes, and the number of items of the column
 #pragma unroll 1
 		for (int g = 0; g < PLAN_GROUPS; ++g) {
-			if (lane == 0) { mm[g] = 0u; ms[g] = 0u; mf[g] = 0u; }
+			if (lane == 0) { mm[g] = 0u; ms[g] = 0u; }
 			if (pass0 + 32 * g >= bz1) continue;   // warp-uniform
 			const uint32_t bz = pass0 + 32 * g + lane;
 			int c = CLS_SKIP;
@@ -335,36 +334,18 @@ __global__ void __launch_bounds__(256, KFB_PLAN_MINBLOCKS) k_integrate_plan2(con
 				q.cls[((size_t) (bz - bz0) * q.bny + by) * q.bnx + bx] = (unsigned char) c;
 			}
 			const unsigned int m_mixed = __ballot_sync(0xffffffffu, c >= CLS_MIXED_IN), m_starts = item_starts(m_mixed, lane, INT_MIXED_CAP);
-			const unsigned int m_free = __ballot_sync(0xffffffffu, c == CLS_FREE);
-			if (lane == 0) { mm[g] = m_mixed; ms[g] = m_starts; mf[g] = m_free; }
+			if (lane == 0) { mm[g] = m_mixed; ms[g] = m_starts; }
 			n_half += __popc(m_starts);
-			n_free += __popc(item_starts(m_free, lane, 2u));
 		}
-		if (n_half == 0 && n_free == 0) continue;
+		if (n_half == 0) continue;
 		// One round trip to the queue counters per column (they are hot: 4096 warps): the column's MIXED items take one
-		// contiguous range, [half 0's items in z order][half 1's items in z order], plus one REPLAY job per half; its FREE
-		// items another range (they need no order).
-		unsigned int base_m = 0, base_r = 0, base_f = 0;
-		if (lane == 0) {
-			if (n_half) { base_m = atomicAdd(q.ctr + 0, n_half * halves); base_r = atomicAdd(q.ctr + 3, halves); }
-			if (n_free) base_f = atomicAdd(q.ctr + 1, n_free);
-		}
+		// contiguous range, [half 0's items in z order][half 1's items in z order], plus one REPLAY job per half.  (The FREE
+		// items are cut along x from the class array by k_integrate_free_runs.)
+		unsigned int base_m = 0, base_r = 0;
+		if (lane == 0) { base_m = atomicAdd(q.ctr + 0, n_half * halves); base_r = atomicAdd(q.ctr + 3, halves); }
 		base_m = __shfl_sync(0xffffffffu, base_m, 0);
 		base_r = __shfl_sync(0xffffffffu, base_r, 0);
-		base_f = __shfl_sync(0xffffffffu, base_f, 0);
 		__syncwarp();
-		if (n_free) {
-			unsigned int at_f = base_f;
-#pragma unroll 1
-			for (int g = 0; g < PLAN_GROUPS; ++g) {
-				const unsigned int m_free = mf[g];
-				if (m_free == 0u) continue;
-				const unsigned int fs = item_starts(m_free, lane, 2u);
-				if ((fs >> lane) & 1u) q.q_free[at_f + __popc(fs & lt)] = make_uint2(bx | (by << 12), (pass0 + 32 * g + lane) | (item_len(m_free, lane, 2u) << 16));
-				at_f += __popc(fs);
-			}
-		}
-		if (n_half == 0) { __syncwarp(); continue; }
 		if (lane < halves) q.q_replay[base_r + lane] = make_uint4(bx | (by << 12) | (lane << 24), base_m + lane * n_half, n_half, 0u);
 		unsigned int at_m = base_m;
 		__syncwarp();
@@ -409,6 +390,41 @@ __global__ void __launch_bounds__(256, KFB_PLAN_MINBLOCKS) k_integrate_plan2(con
 			at_m += __popc(m_starts);
 		}
 		__syncwarp();
+	}
+}
+
+// FREE items are cut ALONG X: a row of `len` consecutive FREE bricks is len * 32 contiguous bytes per voxel row, and DRAM
+// wants long contiguous bursts — single bricks (32 bytes per row, rows 2-8 KB apart) streamed at only ~25 % of the HBM
+// rate.  One warp per (by, bz) row of bricks, lanes over bx; runs are decomposed into aligned power-of-two pieces of at
+// most 16 bricks (index arithmetic by shifts in the run kernel; 32 KB per item keeps the tail short).
+//   FREE  { bx_first | by << 12 | log2(len) << 24,  bz }
+__global__ void __launch_bounds__(256) k_integrate_free_runs(const __grid_constant__ Integrate2Params q) {
+	const IntegrateParams& p = q.b;
+	if (p.dev && __ldcg(&p.dev->do_integrate) == 0) return;
+	const uint32_t lane = threadIdx.x, by = blockIdx.x, bz_rel = blockIdx.y * blockDim.y + threadIdx.y;   // warp-uniform
+	const uint32_t bz0 = p.z_begin >> 3, bz1 = (p.z_end + 7) >> 3;
+	if (bz0 + bz_rel >= bz1) return;
+	const unsigned char* row = q.cls + ((size_t) bz_rel * q.bny + by) * q.bnx;
+	for (uint32_t base = 0; base < q.bnx; base += 32) {
+		const uint32_t bx = base + lane;
+		const unsigned int m = __ballot_sync(0xffffffffu, bx < q.bnx && __ldg(row + bx) == CLS_FREE);
+		if (m == 0u) continue;
+		// lane l starts a piece of 2^k bricks when l is a multiple of 2^k, bits l .. l + 2^k - 1 are set, and l is not inside
+		// a larger aligned piece: the largest k that fits at the aligned position wins
+		int k_here = -1;   // log2 of the piece starting at this lane
+		bool covered = false;
+#pragma unroll
+		for (int k = 4; k >= 0; --k) {
+			const unsigned int len = 1u << k, al = lane & ~(len - 1u);
+			const unsigned int need = ((len == 32u) ? 0xffffffffu : ((1u << len) - 1u)) << al;
+			const bool full = (m & need) == need;            // the aligned block of 2^k bricks that contains this lane is all FREE
+			if (full && !covered) { covered = true; if (al == lane) k_here = k; }
+		}
+		const unsigned int starts = __ballot_sync(0xffffffffu, k_here >= 0);
+		unsigned int slot = 0;
+		if (lane == 0) slot = atomicAdd(q.ctr + 1, (unsigned int) __popc(starts));
+		slot = __shfl_sync(0xffffffffu, slot, 0);
+		if (k_here >= 0) q.q_free[slot + __popc(starts & ((1u << lane) - 1u))] = make_uint2(bx | (by << 12) | ((uint32_t) k_here << 24), bz0 + bz_rel);
 	}
 }
 
@@ -522,38 +538,34 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 		idx = is_free ? it : it - n_free;
 #endif
 		if (is_free) {
-			// ---------------- FREE item: 1 or 2 bricks (bx, by, bz ..): per instruction 2 slices x 8 rows x 2 half-rows of 4 voxels
+			// ---------------- FREE item: 2^k bricks along x in brick row (by, bz): 64 voxel rows of 2^k * 32 contiguous bytes
 			const uint2 item = __ldcg(q.q_free + idx);
-			const uint32_t bx = item.x & 0xfffu, by = (item.x >> 12) & 0xfffu;
-			const uint32_t z0 = (item.y & 0xffffu) * 8, z1 = min(p.z_end, z0 + (item.y >> 16) * 8);
-			const uint32_t yy = by * 8 + ((lane >> 1) & 7);
-			uint4* base = reinterpret_cast<uint4*>(p.vol + (size_t) (bx * 8 + (lane & 1) * 4) + (size_t) yy * p.sx) + (size_t) (lane >> 4) * (plane / 4);
-			const bool row_ok = yy < p.sy;
-			// the second brick (64 sectors of 8 voxels) is pulled into L2 while the first is processed: 2 sectors per lane
-			if (z0 + 8 < z1) {
-				const uint32_t pr = by * 8 + (lane & 7);
-#pragma unroll
-				for (int k = 0; k < 2; ++k) {
-					const uint32_t zz = z0 + 8 + (lane >> 3) + 4 * k;
-					if (pr < p.sy && zz < z1)
-						asm volatile("prefetch.global.L2 [%0];" ::"l"(p.vol + (size_t) (bx * 8) + (size_t) pr * p.sx + (size_t) (zz - p.z_begin) * plane));
-				}
-			}
-			for (uint32_t z = z0; z < z1; z += 8) {
+			const uint32_t bx0 = item.x & 0xfffu, by = (item.x >> 12) & 0xfffu, lg = item.x >> 24, bz = item.y;
+			const uint32_t lg_row = lg + 1;                         // log2 of the uint4 (4 voxels) per voxel row
+			const uint32_t total = 64u << lg_row;                   // uint4 of the item
+			uint4* base = reinterpret_cast<uint4*>(p.vol + (size_t) bx0 * 8 + (size_t) (by * 8) * p.sx + (size_t) (bz * 8 - p.z_begin) * plane);
+			const uint32_t sx4 = p.sx >> 2;                         // uint4 per volume row
+			const size_t plane4 = plane >> 2;
+#pragma unroll 1
+			for (uint32_t b0 = 0; b0 < total; b0 += 128) {          // 4 x 32 uint4 in flight per warp
 				uint4 v[4];
+				uint4* ptr[4];
 				bool ok[4];
 #pragma unroll
 				for (int k = 0; k < 4; ++k) {
-					const uint32_t zz = z + 2 * k + (lane >> 4);
-					ok[k] = row_ok && zz < z1;
-					if (ok[k]) v[k] = __ldcs(base + (size_t) (z + 2 * k - p.z_begin) * (plane / 4));
+					const uint32_t e = b0 + 32 * k + lane;
+					const uint32_t r = e >> lg_row, cidx = e & ((1u << lg_row) - 1u);   // voxel row (y + 8 z) and position in it
+					const uint32_t yy = by * 8 + (r & 7u), zz = bz * 8 + (r >> 3);
+					ok[k] = e < total && yy < p.sy && zz < p.z_end;
+					ptr[k] = base + (size_t) (r >> 3) * plane4 + (size_t) (r & 7u) * sx4 + cidx;
+					if (ok[k]) v[k] = __ldcs(ptr[k]);
 				}
 #pragma unroll
 				for (int k = 0; k < 4; ++k)
 					if (ok[k]) {
 						v[k].x = tsdf_update_free(v[k].x, p.maxweight, q.maxw_i, rcp); v[k].y = tsdf_update_free(v[k].y, p.maxweight, q.maxw_i, rcp);
 						v[k].z = tsdf_update_free(v[k].z, p.maxweight, q.maxw_i, rcp); v[k].w = tsdf_update_free(v[k].w, p.maxweight, q.maxw_i, rcp);
-						__stcs(base + (size_t) (z + 2 * k - p.z_begin) * (plane / 4), v[k]);
+						__stcs(ptr[k], v[k]);
 						updated += 4;
 					}
 			}

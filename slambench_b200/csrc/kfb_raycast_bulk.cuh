@@ -1,6 +1,6 @@
 // EXPERIMENT (north_star item 5, "TMA-staged bricks"): raycastKernel with the bricks along the
 // fine-march segment staged into shared memory by the bulk-async copy engine (cp.async.bulk + mbarrier: UBLKCP in SASS)
-// instead of being gathered tap by tap with __ldg.  Selected with KFB_RAY_BULK=1; results are bit-identical to k_raycast
+// instead of being gathered tap by tap with __ldg (also across z-slabs: a row is copied from its owner).  Selected with KFB_RAY_BULK=1; results are bit-identical to k_raycast
 // (same taps, same arithmetic — tests/test_gpu_kernels.py runs both), the numbers are in profiles/r2_summary.md.
 //
 // A warp marches its 8x4 pixel tile in lockstep.  Whenever some lane's sample lies in a FLAGGED brick (the only samples
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY, 8) k_raycast_bulk(RaycastParam
 					__syncwarp();
 					for (int r = (int) lane; r < ny * nz; r += 32) {
 						const int rz = r / ny, ry = r - rz * ny;
-						const short2* src = v.slab_ptr[0] + (size_t) ox + (size_t) (oy + ry) * v.sx + (size_t) (oz + rz) * v.sx * v.sy;
+						const short2* src = vol_plane(v, oz + rz) + (size_t) ox + (size_t) (oy + ry) * v.sx;   // the slice's owner: maybe a peer (NVLink)
 						asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
 								::"r"(smem_u32(brick + (rz * 9 + ry) * RB_ROW)), "l"(src), "r"(row_bytes), "r"(bar) : "memory");
 					}
@@ -139,6 +139,10 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY, 8) k_raycast_bulk(RaycastParam
 					else st3(p.normal, idx, knormalize(surfNorm));
 				} else { st3(p.vertex, idx, f3(0, 0, 0)); st3(p.normal, idx, f3(KFB_INVALID, 0, 0)); }
 			} else { st3(p.vertex, idx, f3(0, 0, 0)); st3(p.normal, idx, f3(KFB_INVALID, 0, 0)); }
+			if (p.n_peer) {   // z-slab group: the pixel as it stands in this rank's maps goes to every peer (see k_raycast)
+				const float3 vv = ld3(p.vertex, idx), nn = ld3(p.normal, idx);
+				for (int i = 0; i < p.n_peer; ++i) { st3(p.peer_vertex[i], idx, vv); st3(p.peer_normal[i], idx, nn); }
+			}
 		}
 	}
 	if (bulk_stats) {

@@ -101,6 +101,36 @@ def slab_bounds(n_z: int, world: int, weights=None, align: int = 1) -> list[tupl
     return [(cuts[r], cuts[r + 1]) for r in range(world)]
 
 
+def equalise_slabs(density, world: int, align: int = 8) -> list[tuple[int, int]]:
+    """Boundaries (multiples of `align`, at least `align` slices per slab) that give every slab the same share of `density`."""
+    n_z = len(density)
+    cum = np.concatenate([[0.0], np.cumsum(np.asarray(density, np.float64))])
+    cuts = [0]
+    for r in range(1, world):
+        z = int(np.searchsorted(cum, cum[-1] * r / world))
+        z = int(round(z / align)) * align
+        z = min(max(z, cuts[-1] + align), n_z - (world - r) * align)
+        cuts.append(z)
+    cuts.append(n_z)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def refit_density(density, slabs, times):
+    """One step of iterative proportional fitting: inside every slab the per-slice cost density keeps its shape and is
+    scaled so that it sums to the slab's MEASURED integrate time.  Starting from the a-priori model
+    (frustum_slice_weights) a few rounds of measure -> refit -> equalise_slabs balance the slabs on what the camera really
+    sees; a volume does not depend on how it is cut."""
+    d = np.array(density, np.float64) + 1e-12
+    for (a, b), t in zip(slabs, times):
+        d[a:b] *= max(float(t), 1e-9) / d[a:b].sum()
+    return d
+
+
+def rebalance_slabs(slabs, times, align: int = 8) -> list[tuple[int, int]]:
+    """New boundaries from ONE measurement with a flat density inside every slab (see refit_density for the iterated form)."""
+    return equalise_slabs(refit_density(np.ones(slabs[-1][1]), slabs, times), len(slabs), align)
+
+
 def frustum_slice_weights(n_z: int, volume_dim: float, pose, k, image_wh, far: float = 4.0, mu: float = 0.1):
     """Expected integrate work per z-slice for a camera at `pose` that sees surfaces around depth `far`: the area of the
     slice that projects into the image, weighted by what integrate does there (cpp/kernels.cpp:647-661 as k_integrate_run2
@@ -146,7 +176,7 @@ class ShardedKfusion:
 
     def __init__(self, inputSize, volumeResolution, volumeDimensions, initPose, pyramid=(10, 5, 4), *, rank: int, world: int,
                  device: int = 0, icp_mode: str = "replicated", dist=None, local_factory=None, flags: int = 0,
-                 balance_k=None, balance_far: float = 4.0, transport: str = "peer"):
+                 balance_k=None, balance_far: float = 4.0, transport: str = "peer", slabs=None):
         if dist is None:
             import torch.distributed as dist  # noqa: PLC0415
         import torch  # noqa: PLC0415
@@ -167,7 +197,7 @@ class ShardedKfusion:
             vd = float(volumeDimensions) if np.isscalar(volumeDimensions) else float(volumeDimensions[2])
             weights = frustum_slice_weights(vr[2], vd, pose0, balance_k, (int(inputSize[0]), int(inputSize[1])), far=balance_far)
         # every slab starts on a brick layer (8 slices): integrate classifies and the raycaster skips per 8^3 brick
-        self.slabs = slab_bounds(vr[2], world, weights, align=8)
+        self.slabs = [tuple(int(v) for v in z) for z in slabs] if slabs is not None else slab_bounds(vr[2], world, weights, align=8)
         self.bands = row_bands(int(inputSize[1]), world)
         self.pyramid = tuple(int(i) for i in pyramid)
         make = local_factory or (lambda **kw: kf.Kfusion(inputSize, vr, volumeDimensions, initPose, self.pyramid, **kw))
