@@ -206,11 +206,15 @@ static inline Mat4 toMat(const float* m) { Mat4 r; memcpy(r.m, m, sizeof r.m); r
 // every enqueue on the main stream ends the window in which the next frame's preprocessing may overlap (see kfb_ctx::side)
 #define LAUNCHED(c) ((c)->st.kernel_launches++, (c)->overlap_ok = false, (c)->side_pending = false)
 
+// brick flags + super-brick flags (one allocation)
+static size_t brick_bytes(const kfb_ctx* c) {
+	return c->brick.n_bricks + (size_t) c->brick.snx * c->brick.sny * ((c->brick.bnz + 7) / 8);
+}
 static int launch_init_volume(kfb_ctx* c) {
 	const size_t n = c->slab_voxels, n4 = n / 4;
 	k_init_volume<<<148 * 8, 256, 0, c->stream>>>((uint4*) c->d_vol, n4, c->d_vol, n);
 	LAUNCHED(c);
-	if (c->brick.flag) CK(cudaMemsetAsync(c->brick.flag, 0, (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz, c->stream));   // 32766 everywhere
+	if (c->brick.flag) CK(cudaMemsetAsync(c->brick.flag, 0, brick_bytes(c), c->stream));   // 32766 everywhere: bricks and super-bricks clear
 	CK(cudaGetLastError());
 	return 0;
 }
@@ -432,8 +436,11 @@ static int create_impl(const kfb_config* cfg, kfb_ctx* c) {
 	const bool whole = (c->z0 == 0 && c->z1 == cfg->volume_res[2]);
 	if ((whole || (c->cfg.flags & KFB_FLAG_BRICKS_MERGED)) && !(c->cfg.flags & KFB_FLAG_RAYCAST_NO_SKIP)) {
 		c->brick.bnx = (cfg->volume_res[0] + 7) / 8; c->brick.bny = (cfg->volume_res[1] + 7) / 8; c->brick.bnz = (cfg->volume_res[2] + 7) / 8;
-		CK(cudaMalloc(&c->brick.flag, (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz));
+		c->brick.n_bricks = (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz;
+		c->brick.snx = (c->brick.bnx + 7) / 8; c->brick.sny = (c->brick.bny + 7) / 8;
+		CK(cudaMalloc(&c->brick.flag, brick_bytes(c)));
 		c->view_all.brick = c->brick.flag; c->view_all.bnx = c->brick.bnx; c->view_all.bny = c->brick.bny;
+		c->view_all.super = c->brick.flag + c->brick.n_bricks; c->view_all.snx = c->brick.snx; c->view_all.sny = c->brick.sny;
 	}
 	int rc = launch_init_volume(c);
 	if (rc) return rc;
@@ -881,7 +888,7 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 		for (int r = 0; r < c->world; ++r) if (r != c->rank && c->peer_bricks[r]) p.brick.peer[p.brick.n_peer++] = c->peer_bricks[r];
 	if (maxweight > 200.f && c->brick.flag) {
 		// the flagging rule in k_integrate_run assumes w + 1 <= 201; beyond that stop using (and maintaining) the flags
-		c->view_all.brick = nullptr; p.brick.flag = nullptr; c->brick_off = true;
+		c->view_all.brick = nullptr; c->view_all.super = nullptr; p.brick.flag = nullptr; c->brick_off = true;
 	}
 	if (c->brick_off) p.brick.flag = nullptr;
 	p.dmax = (c->dmax_slot >= 0) ? reinterpret_cast<const float*>(c->d_dmax + c->dmax_slot) : nullptr;
@@ -1287,7 +1294,7 @@ int kfb_write_buffer(kfb_ctx* c, int which, int level, const void* src, size_t b
 	CK(cudaStreamSynchronize(c->stream));
 	CK(cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice));
 	if (which == KFB_BUF_VOLUME && c->brick.flag) {   // the flags must describe the volume the raycaster will read
-		CK(cudaMemsetAsync(c->brick.flag, 0, (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz, c->stream));
+		CK(cudaMemsetAsync(c->brick.flag, 0, brick_bytes(c), c->stream));
 		k_brick_rebuild<<<148 * 8, 256, 0, c->stream>>>(c->brick, c->d_vol, c->cfg.volume_res[0], c->cfg.volume_res[1], c->z1 - c->z0, c->z0);
 		LAUNCHED(c);
 		CK(cudaGetLastError());
@@ -1347,6 +1354,7 @@ int kfb_slab_import(kfb_ctx* c, int rank, int world, const uint8_t* handles64, c
 	if (world > 1) { c->overlap_enabled = false; c->overlap_ok = false; c->side_pending = false; }
 	// each rank flags only what ITS slices touch: without the caller's merge the raycaster must not skip
 	if (!(c->cfg.flags & KFB_FLAG_BRICKS_MERGED)) c->view_all.brick = nullptr;
+	c->view_all.super = nullptr;   // the caller merges the brick flags only (KFB_BUF_BRICKFLAGS): no coarse leaps over peers' slabs
 	for (int r = 0; r < world; ++r) {
 		c->view_all.slab_z[r] = z_begin[r];
 		if (r == rank) { c->view_all.slab_ptr[r] = c->d_vol; continue; }
@@ -1388,7 +1396,7 @@ int kfb_ipc_import(kfb_ctx* c, int rank, int world, const kfb_ipc_handles* all) 
 	if (world > 1) { c->overlap_enabled = false; c->overlap_ok = false; c->side_pending = false; }
 	bool all_bricks = c->brick.flag != nullptr;
 	for (int r = 0; r < world; ++r) all_bricks = all_bricks && all[r].has_bricks;
-	if (!all_bricks) c->view_all.brick = nullptr;       // without every rank's flags the raycaster must not skip
+	if (!all_bricks) { c->view_all.brick = nullptr; c->view_all.super = nullptr; }   // without every rank's flags the raycaster must not skip
 	auto open = [&](const uint8_t* h64, void** out) -> int {
 		cudaIpcMemHandle_t h;
 		memcpy(&h, h64, 64);

@@ -689,7 +689,7 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 						if (ddy) m &= (half == 0) ? 0x000000ffu : 0u;  // lanes with y % 8 == 0
 						const uint32_t bz = (uint32_t) z >> BRICK_SHIFT;
 						if (m && bx >= ddx && by >= ddy && bz >= ddz)
-							brick_set(p.brick, ((size_t) (bz - ddz) * p.brick.bny + (by - ddy)) * p.brick.bnx + (bx - ddx));
+							brick_set(p.brick, bx - ddx, by - ddy, bz - ddz);
 					}
 				}
 			}

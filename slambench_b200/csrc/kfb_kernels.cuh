@@ -773,14 +773,21 @@ __global__ void __launch_bounds__(ICP_THREADS, 512 / ICP_THREADS) k_icp(const __
 struct BrickMap {
 	unsigned char* flag;     // [bnz][bny][bnx]; nullptr = not maintained
 	uint32_t bnx, bny, bnz;
+	// second level, same rule one octave up: one byte per 8^3 BRICKS (64^3 voxels), set whenever one of its bricks is.  It
+	// lives right behind the brick flags in the same allocation (so a peer's copy is found the same way): the raycaster
+	// leaps whole runs of COARSE steps through a clear super-brick (raycast_one).
+	size_t n_bricks;         // bnx * bny * bnz: offset of the super-brick flags
+	uint32_t snx, sny;
 	// z-slab mode over peer memory: every rank keeps a map of the WHOLE volume, and a rank that flags a brick of its slab
 	// stores the byte into all peers' maps as well (NVLink P2P; "set to 1" is idempotent, so there is nothing to merge)
 	unsigned char* peer[KFB_MAX_SLABS - 1];
 	int n_peer;
 };
-__device__ __forceinline__ void brick_set(const BrickMap& b, size_t idx) {
-	b.flag[idx] = 1;
-	for (int i = 0; i < b.n_peer; ++i) b.peer[i][idx] = 1;
+__device__ __forceinline__ void brick_set(const BrickMap& b, uint32_t bx, uint32_t by, uint32_t bz) {
+	const size_t idx = ((size_t) bz * b.bny + by) * b.bnx + bx;
+	const size_t sidx = b.n_bricks + ((size_t) (bz >> 3) * b.sny + (by >> 3)) * b.snx + (bx >> 3);
+	b.flag[idx] = 1; b.flag[sidx] = 1;
+	for (int i = 0; i < b.n_peer; ++i) { b.peer[i][idx] = 1; b.peer[i][sidx] = 1; }
 }
 __device__ __noinline__ void brick_mark(const BrickMap b, uint32_t x, uint32_t y, uint32_t z) {
 	const uint32_t bx1 = x >> BRICK_SHIFT, by1 = y >> BRICK_SHIFT, bz1 = z >> BRICK_SHIFT;
@@ -789,8 +796,7 @@ __device__ __noinline__ void brick_mark(const BrickMap b, uint32_t x, uint32_t y
 	for (uint32_t bz = bz0; bz <= bz1; ++bz)
 		for (uint32_t by = by0; by <= by1; ++by)
 			for (uint32_t bx = bx0; bx <= bx1; ++bx) {
-				const size_t idx = ((size_t) bz * b.bny + by) * b.bnx + bx;
-				if (b.flag[idx] == 0) brick_set(b, idx);
+				if (b.flag[((size_t) bz * b.bny + by) * b.bnx + bx] == 0) brick_set(b, bx, by, bz);
 			}
 }
 // rebuild from a volume (after kfb_write_buffer / for tests)
@@ -1076,7 +1082,7 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run(Integr
 						const uint32_t by1 = y >> BRICK_SHIFT, by0 = (((y & 7u) == 0u) && y) ? by1 - 1 : by1;
 						const uint32_t bz1 = (uint32_t) z >> BRICK_SHIFT, bz0 = (first && bz1) ? bz1 - 1 : bz1;
 						for (uint32_t bz = bz0; bz <= bz1; ++bz)
-							for (uint32_t by = by0; by <= by1; ++by) brick_set(p.brick, ((size_t) bz * p.brick.bny + by) * p.brick.bnx + bx);
+							for (uint32_t by = by0; by <= by1; ++by) brick_set(p.brick, bx, by, bz);
 					}
 				}
 			}
@@ -1116,6 +1122,8 @@ struct VolView {
 	int fastdiv;
 	const unsigned char* brick;   // brick flags (see BrickMap) or nullptr
 	uint32_t bnx, bny;
+	const unsigned char* super;   // super-brick flags (64^3 voxels each) or nullptr: coarse steps are then taken one by one
+	uint32_t snx, sny;
 	int no_leap;                  // A/B switch (KFB_RAY_NO_LEAP=1): take every fine step through clear bricks one by one
 };
 
@@ -1211,19 +1219,26 @@ __device__ __forceinline__ float3 vol_grad(const VolView& v, float3 pos) {  // c
 	const int ux = kmini(bx + 1, mx), uy = kmini(by + 1, my), uz = kmini(bz + 1, mz);     // upper_lower == upper
 	const int uux = kmini(bx + 2, mx), uuy = kmini(by + 2, my), uuz = kmini(bz + 2, mz);  // upper_upper
 	float3 g;
-#define VS(a, b, c) vol_vs2(v, a, b, c)
-	g.x = (((VS(ux, ly, lz) - VS(llx, ly, lz)) * (1 - f.x) + (VS(uux, ly, lz) - VS(lx, ly, lz)) * f.x) * (1 - f.y)
-			+ ((VS(ux, uy, lz) - VS(llx, uy, lz)) * (1 - f.x) + (VS(uux, uy, lz) - VS(lx, uy, lz)) * f.x) * f.y) * (1 - f.z)
-			+ (((VS(ux, ly, uz) - VS(llx, ly, uz)) * (1 - f.x) + (VS(uux, ly, uz) - VS(lx, ly, uz)) * f.x) * (1 - f.y)
-					+ ((VS(ux, uy, uz) - VS(llx, uy, uz)) * (1 - f.x) + (VS(uux, uy, uz) - VS(lx, uy, uz)) * f.x) * f.y) * f.z;
-	g.y = (((VS(lx, uy, lz) - VS(lx, lly, lz)) * (1 - f.x) + (VS(ux, uy, lz) - VS(ux, lly, lz)) * f.x) * (1 - f.y)
-			+ ((VS(lx, uuy, lz) - VS(lx, ly, lz)) * (1 - f.x) + (VS(ux, uuy, lz) - VS(ux, ly, lz)) * f.x) * f.y) * (1 - f.z)
-			+ (((VS(lx, uy, uz) - VS(lx, lly, uz)) * (1 - f.x) + (VS(ux, uy, uz) - VS(ux, lly, uz)) * f.x) * (1 - f.y)
-					+ ((VS(lx, uuy, uz) - VS(lx, ly, uz)) * (1 - f.x) + (VS(ux, uuy, uz) - VS(ux, ly, uz)) * f.x) * f.y) * f.z;
-	g.z = (((VS(lx, ly, uz) - VS(lx, ly, llz)) * (1 - f.x) + (VS(ux, ly, uz) - VS(ux, ly, llz)) * f.x) * (1 - f.y)
-			+ ((VS(lx, uy, uz) - VS(lx, uy, llz)) * (1 - f.x) + (VS(ux, uy, uz) - VS(ux, uy, llz)) * f.x) * f.y) * (1 - f.z)
-			+ (((VS(lx, ly, uuz) - VS(lx, ly, lz)) * (1 - f.x) + (VS(ux, ly, uuz) - VS(ux, ly, lz)) * f.x) * (1 - f.y)
-					+ ((VS(lx, uy, uuz) - VS(lx, uy, lz)) * (1 - f.x) + (VS(ux, uy, uuz) - VS(ux, uy, lz)) * f.x) * f.y) * f.z;
+	// the 32 taps come from 4 slices x 4 rows x 4 columns: slice bases (each maybe in a peer's slab) and row offsets once,
+	// then every tap is two adds away (vol_vs2 recomputes a 64-bit index per tap)
+	const short2* Pll = vol_plane(v, llz);
+	const short2* Pl = vol_plane(v, lz);
+	const short2* Pu = vol_plane(v, uz);
+	const short2* Puu = vol_plane(v, uuz);
+	const uint32_t Rll = (uint32_t) lly * v.sx, Rl = (uint32_t) ly * v.sx, Ru = (uint32_t) uy * v.sx, Ruu = (uint32_t) uuy * v.sx;
+#define VS(X, R, P) ((float) __ldg(reinterpret_cast<const short*>((P) + ((R) + (uint32_t) (X)))))
+	g.x = (((VS(ux, Rl, Pl) - VS(llx, Rl, Pl)) * (1 - f.x) + (VS(uux, Rl, Pl) - VS(lx, Rl, Pl)) * f.x) * (1 - f.y)
+			+ ((VS(ux, Ru, Pl) - VS(llx, Ru, Pl)) * (1 - f.x) + (VS(uux, Ru, Pl) - VS(lx, Ru, Pl)) * f.x) * f.y) * (1 - f.z)
+			+ (((VS(ux, Rl, Pu) - VS(llx, Rl, Pu)) * (1 - f.x) + (VS(uux, Rl, Pu) - VS(lx, Rl, Pu)) * f.x) * (1 - f.y)
+					+ ((VS(ux, Ru, Pu) - VS(llx, Ru, Pu)) * (1 - f.x) + (VS(uux, Ru, Pu) - VS(lx, Ru, Pu)) * f.x) * f.y) * f.z;
+	g.y = (((VS(lx, Ru, Pl) - VS(lx, Rll, Pl)) * (1 - f.x) + (VS(ux, Ru, Pl) - VS(ux, Rll, Pl)) * f.x) * (1 - f.y)
+			+ ((VS(lx, Ruu, Pl) - VS(lx, Rl, Pl)) * (1 - f.x) + (VS(ux, Ruu, Pl) - VS(ux, Rl, Pl)) * f.x) * f.y) * (1 - f.z)
+			+ (((VS(lx, Ru, Pu) - VS(lx, Rll, Pu)) * (1 - f.x) + (VS(ux, Ru, Pu) - VS(ux, Rll, Pu)) * f.x) * (1 - f.y)
+					+ ((VS(lx, Ruu, Pu) - VS(lx, Rl, Pu)) * (1 - f.x) + (VS(ux, Ruu, Pu) - VS(ux, Rl, Pu)) * f.x) * f.y) * f.z;
+	g.z = (((VS(lx, Rl, Pu) - VS(lx, Rl, Pll)) * (1 - f.x) + (VS(ux, Rl, Pu) - VS(ux, Rl, Pll)) * f.x) * (1 - f.y)
+			+ ((VS(lx, Ru, Pu) - VS(lx, Ru, Pll)) * (1 - f.x) + (VS(ux, Ru, Pu) - VS(ux, Ru, Pll)) * f.x) * f.y) * (1 - f.z)
+			+ (((VS(lx, Rl, Puu) - VS(lx, Rl, Pl)) * (1 - f.x) + (VS(ux, Rl, Puu) - VS(ux, Rl, Pl)) * f.x) * (1 - f.y)
+					+ ((VS(lx, Ru, Puu) - VS(lx, Ru, Pl)) * (1 - f.x) + (VS(ux, Ru, Puu) - VS(ux, Ru, Pl)) * f.x) * f.y) * f.z;
 #undef VS
 	return g * f3(v.dx / (float) v.sx, v.dy / (float) v.sy, v.dz / (float) v.sz) * (0.5f * 0.00003051944088f);
 }
@@ -1262,20 +1277,28 @@ __device__ __forceinline__ float3 raycast_one(const VolView& v, uint32_t px, uin
 					// THIS brick are clear as well, so only the reference's `t += stepsize` is replayed for them (the exact
 					// sequence of t values is kept; nothing else depends on those samples).  A ray that has grazed a surface
 					// walks the rest of its way in fine steps: these are the longest chains of the kernel.
-					if (leap && stepsize == step && c.bx >= 0 && c.by >= 0 && c.bz >= 0 && c.bx < (int) v.sx - 1 && c.by < (int) v.sy - 1 && c.bz < (int) v.sz - 1) {
-						// voxels per unit t along each axis, and the room (in t) to the brick's faces, shrunk by a margin that
-						// dwarfs every rounding involved (positions are exact to ~1e-3 voxel)
-						const float3 ds = f3(direction.x * ((float) v.sx * v.rdx), direction.y * ((float) v.sy * v.rdy), direction.z * ((float) v.sz * v.rdz));
-						const float px_ = (float) (c.bx & 7) + c.fx, py_ = (float) (c.by & 7) + c.fy, pz_ = (float) (c.bz & 7) + c.fz;   // position inside the brick, [0, 8)
-						const float rx = (ds.x > 0.f ? 7.95f - px_ : px_ - 0.05f) * rcp_approx(fabsf(ds.x) + 1e-20f);
-						const float ry = (ds.y > 0.f ? 7.95f - py_ : py_ - 0.05f) * rcp_approx(fabsf(ds.y) + 1e-20f);
-						const float rz = (ds.z > 0.f ? 7.95f - pz_ : pz_ - 0.05f) * rcp_approx(fabsf(ds.z) + 1e-20f);
-						const float room = kminf(kminf(rx, ry), rz);
-						int n = (room > 0.f) ? (int) kminf(room * rcp_approx(stepsize), 64.f) - 1 : 0;
-						while (n > 0) {
-							const float tn = t + stepsize;
-							if (!(tn < tfar)) break;   // the loop's own increment and test end the march
-							t = tn; t_lazy = tn; --n;
+					// The same one level up for COARSE steps: a clear SUPER-brick (64^3 voxels) holds only clear bricks, and a ray
+					// crosses it in several coarse steps — most of the march through free space in front of the surface.
+					if (leap && c.bx >= 0 && c.by >= 0 && c.bz >= 0 && c.bx < (int) v.sx - 1 && c.by < (int) v.sy - 1 && c.bz < (int) v.sz - 1) {
+						const bool fine = stepsize == step;
+						bool region_clear = fine;   // the brick itself is known clear
+						if (!fine && v.super) region_clear = __ldg(v.super + ((((uint32_t) c.bz >> 6) * v.sny + ((uint32_t) c.by >> 6)) * v.snx + ((uint32_t) c.bx >> 6))) == 0;
+						if (region_clear) {
+							const int msk = fine ? 7 : 63;
+							const float hi = fine ? 7.95f : 63.95f;   // the region's far face, less a margin that dwarfs every rounding involved
+							// voxels per unit t along each axis, and the room (in t) to the region's faces (positions are exact to ~1e-3 voxel)
+							const float3 ds = f3(direction.x * ((float) v.sx * v.rdx), direction.y * ((float) v.sy * v.rdy), direction.z * ((float) v.sz * v.rdz));
+							const float px_ = (float) (c.bx & msk) + c.fx, py_ = (float) (c.by & msk) + c.fy, pz_ = (float) (c.bz & msk) + c.fz;   // position inside the region
+							const float rx = (ds.x > 0.f ? hi - px_ : px_ - 0.05f) * rcp_approx(fabsf(ds.x) + 1e-20f);
+							const float ry = (ds.y > 0.f ? hi - py_ : py_ - 0.05f) * rcp_approx(fabsf(ds.y) + 1e-20f);
+							const float rz = (ds.z > 0.f ? hi - pz_ : pz_ - 0.05f) * rcp_approx(fabsf(ds.z) + 1e-20f);
+							const float room = kminf(kminf(rx, ry), rz);
+							int n = (room > 0.f) ? (int) kminf(room * rcp_approx(stepsize), 64.f) - 1 : 0;
+							while (n > 0) {
+								const float tn = t + stepsize;
+								if (!(tn < tfar)) break;   // the loop's own increment and test end the march
+								t = tn; t_lazy = tn; --n;
+							}
 						}
 					}
 					continue;
