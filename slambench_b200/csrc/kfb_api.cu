@@ -69,6 +69,7 @@ struct kfb_ctx {
 	cudaStream_t side;
 	cudaEvent_t ev_window, ev_side_done;
 	bool overlap_enabled, overlap_ok, side_pending;
+	bool window_late;           // the overlap window opens before the raycast, not before the integrate (KFB_WINDOW_EARLY=1: round 1's choice)
 	uint32_t cw, ch;
 	int levels;
 	uint32_t lw[KFB_MAX_LEVELS], lh[KFB_MAX_LEVELS];
@@ -279,6 +280,9 @@ static int create_impl(const kfb_config* cfg, kfb_ctx* c) {
 	CK(cudaEventCreateWithFlags(&c->ev_window, cudaEventDisableTiming));
 	CK(cudaEventCreateWithFlags(&c->ev_side_done, cudaEventDisableTiming));
 	{ const char* e = getenv("KFB_NO_OVERLAP"); c->overlap_enabled = !(e && atoi(e) > 0); }
+	// measured in round 2 (profiles/r2_summary.md): with the brick-classified integrate the early window gives the same fps
+	// (2600 vs 2620) but lets the next frame's preprocessing compete with k_integrate_run2 (133 vs 121 us)
+	{ const char* e = getenv("KFB_WINDOW_EARLY"); c->window_late = !(e && atoi(e) > 0); }
 	c->overlap_ok = false; c->side_pending = false;
 	const size_t P = (size_t) c->cw * c->ch;
 	CK(cudaMalloc(&c->d_vol, c->slab_voxels * sizeof(short2)));
@@ -871,7 +875,7 @@ int kfb_track(kfb_ctx* c, const float k[4], float icp_threshold, uint32_t tracki
 static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, float mu, float maxweight, const DevFrame* dev = nullptr) {
 	// everything the next frame's preprocessing rewrites has been read by now, except the raw depth and its maximum,
 	// which are double- / triple-buffered: its window (kfb_ctx::side) opens here
-	if (c->overlap_enabled) CK(cudaEventRecord(c->ev_window, c->stream));
+	if (c->overlap_enabled && !c->window_late) CK(cudaEventRecord(c->ev_window, c->stream));
 	IntegrateParams p;
 	p.vol = c->d_vol;
 	p.sx = c->cfg.volume_res[0]; p.sy = c->cfg.volume_res[1]; p.sz = c->cfg.volume_res[2];
@@ -969,7 +973,7 @@ static int launch_integrate(kfb_ctx* c, const float* invTrack, const float* K, f
 	CK(cudaGetLastError());
 	c->integrate_count++;
 	if (!dev) c->st.frames_integrated++;   // device-gated launches are counted when the host learns the gate
-	c->overlap_ok = c->overlap_enabled;   // until anything but the raycast is enqueued
+	c->overlap_ok = c->overlap_enabled && !c->window_late;   // until anything but the raycast is enqueued
 	return 0;
 }
 

@@ -192,8 +192,9 @@ __device__ __forceinline__ bool int_geom_load(IntGeom& g, const Integrate2Params
 
 // Class of the box of voxels [x0, x1] x [y0, y1] x [z0, z1] (inclusive), from linear bounds over the box of their centres
 // and its 8 projected corners (see the file header).  FREE is only claimed where the caller may use it (`allow_free`).
+// `quick`: only the linear tests (camera plane, image half-spaces, farthest depth) — SKIP or "cannot tell" (MIXED_EDGE).
 __device__ __noinline__ int classify_box(const Integrate2Params& q, const IntGeom& g, uint32_t x0, uint32_t x1, uint32_t y0, uint32_t y1,
-		uint32_t z0, uint32_t z1, float dmax_all, bool allow_free) {
+		uint32_t z0, uint32_t z1, float dmax_all, bool allow_free, bool quick = false) {
 	const IntegrateParams& p = q.b;
 	const float vx = q.vsz[0], vy = q.vsz[1], vz = q.vsz[2];
 	// box of the voxel CENTRES (Volume::pos, commons.h:186-189): centre and half extents in metres
@@ -233,7 +234,7 @@ __device__ __noinline__ int classify_box(const Integrate2Params& q, const IntGeo
 	}
 	// beyond the farthest depth of the whole image: e < -mu (or depth == 0) for every pixel
 	if (dmax_all + p.mu + (p.mu * 1e-5f + 1e-6f * (dmax_all + cz_max)) < cz_min) return CLS_SKIP;
-	if (!(cz_min >= 0.05f)) return CLS_MIXED_EDGE;                                   // too close to the camera plane for a footprint
+	if (quick || !(cz_min >= 0.05f)) return CLS_MIXED_EDGE;                          // too close to the camera plane for a footprint
 	float umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f;
 #pragma unroll
 	for (int c = 0; c < 8; ++c) {
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(256, KFB_PLAN_MINBLOCKS) k_integrate_plan2(con
 	const unsigned int lt = (1u << lane) - 1u;
 	const uint32_t x0 = bx * 8, x1 = min(x0 + 7, p.sx - 1), y0 = by * 8, y1 = min(y0 + 7, p.sy - 1);
 	// the whole column first (most columns lie outside the view frustum: one test instead of one per brick)
-	if (fast && classify_box(q, geom, x0, x1, y0, y1, p.z_begin, p.z_end - 1, dmax_all, false) == CLS_SKIP) {
+	if (fast && classify_box(q, geom, x0, x1, y0, y1, p.z_begin, p.z_end - 1, dmax_all, false, true) == CLS_SKIP) {
 		for (uint32_t bz = bz0 + lane; bz < bz1; bz += 32) q.cls[((size_t) (bz - bz0) * q.bny + by) * q.bnx + bx] = CLS_SKIP;
 		return;
 	}
@@ -396,7 +397,8 @@ __global__ void __launch_bounds__(256, KFB_PLAN_MINBLOCKS) k_integrate_plan2(con
 // FREE items are cut ALONG X: a row of `len` consecutive FREE bricks is len * 32 contiguous bytes per voxel row, and DRAM
 // wants long contiguous bursts — single bricks (32 bytes per row, rows 2-8 KB apart) streamed at only ~25 % of the HBM
 // rate.  One warp per (by, bz) row of bricks, lanes over bx; runs are decomposed into aligned power-of-two pieces of at
-// most 16 bricks (index arithmetic by shifts in the run kernel; 32 KB per item keeps the tail short).
+// most 16 bricks (index arithmetic by shifts in the run kernel; 32 KB per item keeps the tail short — cutting the rows inside
+// the run kernel instead, one whole brick row per claim, was measured: 81 -> 132 us, the row jobs are too long).
 //   FREE  { bx_first | by << 12 | log2(len) << 24,  bz }
 __global__ void __launch_bounds__(256) k_integrate_free_runs(const __grid_constant__ Integrate2Params q) {
 	const IntegrateParams& p = q.b;
