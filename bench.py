@@ -489,7 +489,7 @@ def sharded_run(args, rank: int, world: int, local_rank: int, torch, dist, volum
     host = torch.from_numpy(depth_np).pin_memory()
     depth_np = host.numpy()
     slabs, calib = None, []
-    if not args.even_slabs and not args.no_calibration:
+    if not args.even_slabs and args.calibrate_slabs:
         # Calibration (set-up, untimed): a few short runs of the first frames; after each, the integrate time of every slab is
         # measured, the per-slice cost density refitted to it (sharded.refit_density) and the boundaries moved so that the
         # slabs cost the same.  The cost of a slice depends on what the camera sees, which no a-priori model knows.
@@ -623,7 +623,8 @@ def main():
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the extra z-slab (configs[3]/[4]) runs")
     ap.add_argument("--sharded-steps", type=int, default=20, help="timed frames of the z-slab runs added to the N > 1 line")
     ap.add_argument("--even-slabs", action="store_true", help="sharded mode: equal z-slabs instead of the load-aware boundaries")
-    ap.add_argument("--no-calibration", action="store_true", help="sharded mode: keep the a-priori slab boundaries (no measured rebalancing pass)")
+    ap.add_argument("--calibrate-slabs", action="store_true",
+                    help="sharded mode: refine the a-priori slab boundaries with measured per-slab integrate times (untimed passes before the run)")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes/launch of k_integrate from the ncu capture in profiles/")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -456,6 +456,59 @@ __device__ __forceinline__ uint32_t tsdf_update_free(uint32_t v, float maxweight
 	return tsdf_update_free_slow(v, maxweight, rcp);
 }
 
+// x <- fl(x + d) applied n times, bit for bit, in O(binades crossed): inside one binade and sign every correctly rounded
+// addition of the same d moves x by the same whole number of ulps (ties included from the second step in the binade on), so
+// after two real steps there the rest is one integer multiply-add on the bit pattern; the step that leaves the binade is taken
+// for real (and a sum that falls just below the binade's floor rounds on the finer grid: stay strictly above it).  Checked
+// against the plain loop on ~6 M random, KinectFusion-like and tie-prone cases: tools/jump_ahead_check.c.  This is what makes
+// the replay of the reference's additions independent of how far up the column a slab starts.
+__device__ __forceinline__ float jump_ahead(float x, float d, int n) {
+	int k = n;
+	while (k > 0) {
+		const float a = __fadd_rn(x, d);
+		if (--k == 0) { x = a; break; }
+		float b = __fadd_rn(a, d);
+		--k;
+		const uint32_t ux = __float_as_uint(x), ua = __float_as_uint(a), ub = __float_as_uint(b);
+		const uint32_t ea = ua >> 23;   // sign + exponent
+		if (k > 0 && (ux >> 23) == ea && (ub >> 23) == ea && (ea & 0xffu) != 0u && (ea & 0xffu) != 0xffu) {
+			const int S = (int) (ub - ua);   // ulps per step (magnitude space: same sign, same exponent)
+			if (S == 0) return b;            // stagnation: every further step returns b
+			const uint32_t M = ub & 0x7fffffffu, lo = (ea & 0xffu) << 23, hi = lo + 0x7fffffu;
+			// steps that stay inside the binade (strictly above its floor when moving down): a float quotient rounded DOWN by a
+			// safe factor instead of an integer division — an underestimate only costs another round of the loop
+			const uint32_t room = S > 0 ? hi - M : ((M == lo) ? 0u : M - lo - 1u);
+			uint32_t m = (uint32_t) (__fdividef((float) room, (float) abs(S)) * 0.9999f);
+			if (m > (uint32_t) k) m = (uint32_t) k;
+			b = __uint_as_float(ub + (uint32_t) ((int) m * S));
+			k -= (int) m;
+		}
+		x = b;
+	}
+	return x;
+}
+// the six running values of a column, `n` slices further.  MEASURED (profiles/r2_summary.md): the exact jump is SLOWER than the
+// plain additions at every distance this code meets — 512^3 (470 slices on average): +25 us per frame; 1024^3 / 2048^3 far
+// slabs on 8 GPUs (920 / 1870 slices): 292 -> 505 us and 1714 -> 2707 us for the slab that holds the surface — each value
+// takes ~11 data-dependent rounds of ~60 instructions and the lanes of a warp diverge, while the replay is 3 packed FADD2
+// per slice with no divergence.  It stays in the tree, switched off, as the record of the experiment (-DINT_JUMP_MIN=640).
+#ifndef INT_JUMP_MIN
+#define INT_JUMP_MIN 0x7fffffff
+#endif
+__device__ __forceinline__ void replay_advance(F2& A, F2& B, F2& C, F2 dA, F2 dB, F2 dC, int n, bool cz_is_pz) {
+	if (n < INT_JUMP_MIN) {
+#pragma unroll 8
+		for (int i = 0; i < n; ++i) { A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC); }
+		return;
+	}
+	const float px = jump_ahead(f2_lo(A), f2_lo(dA), n), py = jump_ahead(f2_hi(A), f2_hi(dA), n);
+	const float pz = jump_ahead(f2_lo(B), f2_lo(dB), n), cx = jump_ahead(f2_hi(B), f2_hi(dB), n);
+	const float cy = jump_ahead(f2_lo(C), f2_lo(dC), n);
+	// K's third row (0, 0, 1, 0): cameraX.z and pos.z start equal and receive the same increments — one value
+	const float cz = cz_is_pz ? pz : jump_ahead(f2_hi(C), f2_hi(dC), n);
+	A = f2_make(px, py); B = f2_make(pz, cx); C = f2_make(cy, cz);
+}
+
 // flag of the REPLAY job that covers slice `za` of column half (bx, by, half): one job per plan pass of 32 * PLAN_GROUPS layers
 __device__ __forceinline__ size_t ready_index(const Integrate2Params& q, uint32_t bx, uint32_t by, uint32_t half, uint32_t za) {
 	const uint32_t pass = ((za >> 3) - (q.b.z_begin >> 3)) / (32u * PLAN_GROUPS);
@@ -472,11 +525,13 @@ __device__ __forceinline__ void integrate_replay_job(const Integrate2Params& q, 
 	F2 A = f2_make(c.pos0.x, c.pos0.y), B = f2_make(c.pos0.z, c.cam0.x), C = f2_make(c.cam0.y, c.cam0.z);
 	const F2 dA = f2_make(c.delta.x, c.delta.y), dB = f2_make(c.delta.z, c.cameraDelta.x), dC = f2_make(c.cameraDelta.y, c.cameraDelta.z);
 	int z = 0;
+	// cameraX.z == pos.z bit for bit when K's third row is (0, 0, 1, 0) AND the two start equal (they do: cam0.z = 0*x + 0*y + 1*z + 0)
+	const bool cz_is_pz = q.std_k && f2_hi(C) == f2_lo(B) && f2_hi(dC) == f2_lo(dB);
 	for (unsigned int k = 0; k < job.z; ++k) {
 		const unsigned int item = job.y + k;
 		const int za = (int) (__ldcg(&q.q_mixed[item].y) & 0xffffu);
-#pragma unroll 8
-		for (; z < za; ++z) { A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC); }
+		replay_advance(A, B, C, dA, dB, dC, za - z, cz_is_pz);
+		z = za;
 		if (item < q.ckpt_cap) {
 			unsigned long long* o = q.ckpt + (size_t) item * 96 + lane;
 			__stcg(o, A.v); __stcg(o + 32, B.v); __stcg(o + 64, C.v);
@@ -619,8 +674,7 @@ __global__ void __launch_bounds__(256, KFB_INT_MINBLOCKS) k_integrate_run2(Integ
 		} else {
 			const IntColumn c = int_column(p, geom.invTrack, x, y);
 			A = f2_make(c.pos0.x, c.pos0.y); B = f2_make(c.pos0.z, c.cam0.x); C = f2_make(c.cam0.y, c.cam0.z);
-#pragma unroll 8
-			for (int z = 0; z < za; ++z) { A = f2_add(A, dA); B = f2_add(B, dB); C = f2_add(C, dC); }
+			replay_advance(A, B, C, dA, dB, dC, za, false);
 		}
 		short2* col = p.vol + (size_t) x + (size_t) y * p.sx + (size_t) ((uint32_t) za - p.z_begin) * plane;
 		// INT_V consecutive slices per step: the decisions first, straight-line (depth gathers hit L1/L2), then the voxel
