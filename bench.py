@@ -489,37 +489,37 @@ def sharded_run(args, rank: int, world: int, local_rank: int, torch, dist, volum
     host = torch.from_numpy(depth_np).pin_memory()
     depth_np = host.numpy()
     slabs, calib = None, []
-    if not args.even_slabs and args.calibrate_slabs:
-        # Calibration (set-up, untimed): a few short runs of the first frames; after each, the integrate time of every slab is
-        # measured, the per-slice cost density refitted to it (sharded.refit_density) and the boundaries moved so that the
-        # slabs cost the same.  The cost of a slice depends on what the camera sees, which no a-priori model knows.
+    if not args.even_slabs and not args.no_slab_tuning:
+        # Set-up (untimed): a few a-priori partitions (sharded.candidate_slabs) are each run on the first frames and the one
+        # with the shortest frame time is kept.  A volume does not depend on how it is cut; what a cut costs does.
         from slambench_b200 import kfusion as kf_
 
         n_cal = min(n, 12)
-        dens = sharded.frustum_slice_weights(volume, VOLUME_DIM, kf_.identity_pose(T0), K, (W_IMG, H_IMG), far=float(depth_np[0].max()) / 1000.0)
-        dens = dens + dens.sum() * 0.02 / volume
-        slabs = sharded.equalise_slabs(dens, world)
-        for it in range(3):
+        cands = sharded.candidate_slabs(volume, world, VOLUME_DIM, kf_.identity_pose(T0), K, (W_IMG, H_IMG), far=float(depth_np[0].max()) / 1000.0)
+        best = None
+        for name, cs in cands.items():
+            if any(cs == c["slabs_t"] for c in calib):
+                continue
             with sharded.ShardedKfusion((W_IMG, H_IMG), volume, VOLUME_DIM, T0, PYRAMID, rank=rank, world=world, device=local_rank,
-                                        icp_mode=args.icp_mode, slabs=slabs) as s:
-                g = s.local
+                                        icp_mode=args.icp_mode, slabs=cs) as s:
+                t0c = 0.0
                 for f in range(n_cal):
                     if f == 4:
                         s.synchroniseDevices()
-                        g.enable_timing(4)
-                        g.reset_stats()
+                        dist.barrier()
+                        torch.cuda.synchronize()
+                        t0c = time.perf_counter()
                     s.preprocessing(depth_np[f]); s.tracking(K, ICP_THRESHOLD, 1, f); s.integration(K, 1, MU, f); s.raycasting(K, MU, f)
                 s.synchroniseDevices()
-                st_c = g.stats()
-                tms = torch.zeros(world, dtype=torch.float64, device=f"cuda:{local_rank}")
-                tms[rank] = st_c["ms_integrate"] / max(1, int(st_c["frames_integrated"]))
-                dist.all_reduce(tms)
-            times = [float(v) for v in tms]
-            calib.append({"slabs": [list(z) for z in slabs], "integrate_us": [round(1e3 * t, 1) for t in times]})
-            if max(times) < 1.08 * (sum(times) / world):
-                break
-            dens = sharded.refit_density(dens, slabs, times)
-            slabs = sharded.equalise_slabs(dens, world)
+                torch.cuda.synchronize()
+                tt = torch.tensor([(time.perf_counter() - t0c) * 1e3 / (n_cal - 4)], dtype=torch.float64, device=f"cuda:{local_rank}")
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            calib.append({"candidate": name, "slabs_t": cs, "slabs": [list(z) for z in cs], "ms_per_frame": round(float(tt[0]), 4)})
+            if best is None or float(tt[0]) < best[0]:
+                best = (float(tt[0]), cs)
+        slabs = best[1]
+        for c in calib:
+            del c["slabs_t"]
     with sharded.ShardedKfusion((W_IMG, H_IMG), volume, VOLUME_DIM, T0, PYRAMID, rank=rank, world=world, device=local_rank,
                                 icp_mode=args.icp_mode, balance_k=None if args.even_slabs else K,
                                 balance_far=float(depth_np[0].max()) / 1000.0, slabs=slabs) as s:
@@ -623,8 +623,8 @@ def main():
     ap.add_argument("--no-sharded", action="store_true", help="N > 1: skip the extra z-slab (configs[3]/[4]) runs")
     ap.add_argument("--sharded-steps", type=int, default=20, help="timed frames of the z-slab runs added to the N > 1 line")
     ap.add_argument("--even-slabs", action="store_true", help="sharded mode: equal z-slabs instead of the load-aware boundaries")
-    ap.add_argument("--calibrate-slabs", action="store_true",
-                    help="sharded mode: refine the a-priori slab boundaries with measured per-slab integrate times (untimed passes before the run)")
+    ap.add_argument("--no-slab-tuning", action="store_true",
+                    help="sharded mode: take the default a-priori slab boundaries instead of timing a few candidate partitions at set-up")
     ap.add_argument("--traffic-bytes", type=float, default=None, help="dram bytes/launch of k_integrate from the ncu capture in profiles/")
     args = ap.parse_args()
     if args.warmup < 3:

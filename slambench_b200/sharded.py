@@ -131,11 +131,12 @@ def rebalance_slabs(slabs, times, align: int = 8) -> list[tuple[int, int]]:
     return equalise_slabs(refit_density(np.ones(slabs[-1][1]), slabs, times), len(slabs), align)
 
 
-def frustum_slice_weights(n_z: int, volume_dim: float, pose, k, image_wh, far: float = 4.0, mu: float = 0.1):
+def frustum_slice_weights(n_z: int, volume_dim: float, pose, k, image_wh, far: float = 4.0, mu: float = 0.1, band_mu: float = 2.5,
+                          band_weight: float = 3.0):
     """Expected integrate work per z-slice for a camera at `pose` that sees surfaces around depth `far`: the area of the
     slice that projects into the image, weighted by what integrate does there (cpp/kernels.cpp:647-661 as k_integrate_run2
     executes it): free space in front of the surface is a streaming update (weight 1), the band around the surface is
-    decided voxel by voxel (weight 3: roughly the measured cost ratio of the two paths), behind it nothing happens (0).  Used once, at
+    decided voxel by voxel (`band_weight`, over a band of `band_mu` * mu either side of `far`), behind it nothing happens (0).  Used once, at
     set-up, to place the slab boundaries; it is only a load-balance heuristic: any partition gives the same voxels."""
     pose = np.asarray(pose, np.float64).reshape(4, 4)
     fx, fy, cx, cy = [float(v) for v in k]
@@ -144,7 +145,7 @@ def frustum_slice_weights(n_z: int, volume_dim: float, pose, k, image_wh, far: f
     g = (np.arange(n) + 0.5) / n * volume_dim
     X, Y = np.meshgrid(g, g)
     Rinv, t = pose[:3, :3].T, pose[:3, 3]
-    band = 2.5 * mu                                            # mu plus the slack of brick-granular decisions, generously
+    band = band_mu * mu                                        # mu plus the slack of brick-granular decisions
     out = np.zeros(n_z)
     for z in range(n_z):
         P = np.stack([X - t[0], Y - t[1], np.full_like(X, (z + 0.5) / n_z * volume_dim - t[2])], -1) @ Rinv.T
@@ -152,7 +153,19 @@ def frustum_slice_weights(n_z: int, volume_dim: float, pose, k, image_wh, far: f
         with np.errstate(divide="ignore", invalid="ignore"):
             u, v = fx * P[..., 0] / d + cx, fy * P[..., 1] / d + cy
         inside = (d > 1e-4) & (u >= 0) & (u <= w - 1) & (v >= 0) & (v <= h - 1)
-        out[z] = np.count_nonzero(inside & (d < far - band)) + 3.0 * np.count_nonzero(inside & (np.abs(d - far) <= band))
+        out[z] = np.count_nonzero(inside & (d < far - band)) + band_weight * np.count_nonzero(inside & (np.abs(d - far) <= band))
+    return out
+
+
+def candidate_slabs(n_z: int, world: int, volume_dim: float, pose, k, image_wh, far: float) -> dict:
+    """A handful of a-priori partitions for `bench.py`'s set-up to try.  What a slab costs is plan + replay (per slab that
+    holds part of the surface band, hardly divisible) + streaming of its free space + per-voxel work of its part of the
+    band; no closed form ranks the partitions reliably on 2, 4 and 8 GPUs alike (measured, profiles/r2_summary.md), so the
+    harness times a few frames on each candidate and keeps the fastest."""
+    out = {"even": slab_bounds(n_z, world, align=8)}
+    for name, (bm, bw) in {"band2.5x3": (2.5, 3.0), "band1.7x3.5": (1.7, 3.5), "band4x1.5": (4.0, 1.5), "band2.5x1": (2.5, 1.0), "band2.5x0.5": (2.5, 0.5)}.items():
+        w = frustum_slice_weights(n_z, volume_dim, pose, k, image_wh, far=far, band_mu=bm, band_weight=bw)
+        out[name] = slab_bounds(n_z, world, w, align=8)
     return out
 
 
