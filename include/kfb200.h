@@ -82,7 +82,7 @@ enum kfb_buffer {
 	KFB_BUF_REDUCTION_DEV = 13, /* float[32] DEVICE copy of the last track+reduce result (multi-GPU all-reduce operand) */
 	KFB_BUF_BRICKFLAGS = 14,  /* uint8[ceil(N/8)^3] brick flags of the WHOLE volume (see KFB_FLAG_BRICKS_MERGED)            */
 	KFB_BUF_BRICKCLASS = 16,  /* uint8[ceil(slab/8)][ceil(N/8)][ceil(N/8)] classes of the LAST integrate's bricks: 0 skip, 1 free (sdf == 1), 2 per-voxel */
-	KFB_BUF_RAYTILECOST = 15  /* uint32[ceil(h/4)][ceil(w/8)] SM cycles per raycast tile, last launch (env KFB_RAY_TILECOST=1)   */
+	KFB_BUF_RAYTILECOST = 15  /* uint32[ceil(h/4)][ceil(w/8)] SM cycles per raycast tile, last launch                          */
 };
 
 int kfb_abi_version(void);

@@ -123,7 +123,9 @@ struct kfb_ctx {
 	int int_grid, int_grid2;    // persistent CTAs of k_integrate_run / k_integrate_run2
 	int ray_grid;               // persistent CTAs of k_raycast
 	unsigned int* d_tile_ctr;   // two alternating tile counters
-	unsigned int* d_tile_cost;  // KFB_RAY_TILECOST=1: cycles per raycast tile of the last launch (diagnostics)
+	unsigned int* d_tile_cost;  // raycast schedule (RaySched): cost[tiles], stamp[tiles], slow[3][tiles], n[3], sum[3]
+	uint32_t ray_tiles_cap;
+	int ray_sched;              // slow tiles first (KFB_RAY_NO_SCHED=1: index order)
 	uint64_t ray_launches;
 	bool ray_bulk; unsigned int* d_bulk_stats; int ray_bulk_grid;   // KFB_RAY_BULK=1: the bulk-async (TMA engine) staging experiment
 	uint64_t int_launches;
@@ -344,7 +346,10 @@ static int create_impl(const kfb_config* cfg, kfb_ctx* c) {
 	CK(cudaMemsetAsync(c->d_dmax, 0, 3 * sizeof(unsigned int), c->stream));
 	c->dmax_slot = -1; c->preprocess_count = 0;
 	{ const char* e = getenv("KFB_INT_ZCHUNK"); c->int_zchunk = e ? (uint32_t) atoi(e) : 0; }
-	if (getenv("KFB_RAY_TILECOST")) CK(cudaMalloc(&c->d_tile_cost, (size_t) ((c->cw + 7) / 8) * ((c->ch + 3) / 4) * sizeof(unsigned int)));
+	c->ray_tiles_cap = ((c->cw + 7) / 8) * ((c->ch + 3) / 4);
+	c->ray_sched = getenv("KFB_RAY_NO_SCHED") ? 0 : 1;
+	CK(cudaMalloc(&c->d_tile_cost, ((size_t) c->ray_tiles_cap * 5 + 8) * sizeof(unsigned int)));
+	CK(cudaMemsetAsync(c->d_tile_cost, 0, ((size_t) c->ray_tiles_cap * 5 + 8) * sizeof(unsigned int), c->stream));
 	CK(cudaMalloc(&c->d_tile_ctr, 2 * sizeof(unsigned int)));
 	CK(cudaMemsetAsync(c->d_tile_ctr, 0, 2 * sizeof(unsigned int), c->stream));
 	{
@@ -1011,11 +1016,19 @@ int kfb_integrate(kfb_ctx* c, const float k[4], uint32_t integration_rate, float
 static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP, float step, float largestep, const float* view_dev = nullptr) {
 	RaycastParams p;
 	p.view_dev = view_dev;
-	p.n_peer = 0;
-	if (c->peer_mode)
-		for (int r = 0; r < c->world; ++r) if (r != c->rank) { p.peer_vertex[p.n_peer] = c->peer_vertex[r]; p.peer_normal[p.n_peer] = c->peer_normal[r]; ++p.n_peer; }
 	p.vol = c->view_all;
-	p.tile_cost = c->d_tile_cost;
+	{
+		const uint32_t cap = c->ray_tiles_cap;
+		const uint64_t L64 = c->ray_launches + 1;
+		const unsigned int L = (unsigned int) L64, cur = (unsigned int) (L64 % 3), nxt = (unsigned int) ((L64 + 1) % 3), zero = (unsigned int) ((L64 + 2) % 3);
+		unsigned int* base = c->d_tile_cost;
+		unsigned int* ctr = base + (size_t) cap * 5;   // n[3], sum[3]
+		p.sched.cost = base; p.sched.stamp = base + cap;
+		p.sched.slow_cur = base + (size_t) cap * (2 + cur); p.sched.slow_next = base + (size_t) cap * (2 + nxt);
+		p.sched.n_cur = ctr + cur; p.sched.n_next = ctr + nxt; p.sched.n_zero = ctr + zero;
+		p.sched.sum_cur = ctr + 3 + cur; p.sched.sum_next = ctr + 3 + nxt; p.sched.sum_zero = ctr + 3 + zero;
+		p.sched.launch = L; p.sched.enabled = c->ray_sched;
+	}
 	p.vertex = c->d_vertex; p.normal = c->d_normal;
 	p.w = c->cw; p.h = c->ch;
 	p.row0 = c->band0; p.row1 = c->band1;
@@ -1028,6 +1041,22 @@ static int launch_raycast(kfb_ctx* c, const float* view, float nearP, float farP
 	if (c->ray_bulk) k_raycast_bulk<<<c->ray_bulk_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p, c->d_bulk_stats);
 	else k_raycast<<<c->ray_grid, RCK_BX * RCK_BY, 0, c->stream>>>(p);
 	LAUNCHED(c);
+	if (c->peer_mode && c->world > 1) {
+		// the band this rank just wrote goes to every peer's maps (bands are whole rows: one contiguous block per map)
+		const size_t off = (size_t) c->band0 * c->cw * 3 * sizeof(float), bytes = (size_t) (c->band1 - c->band0) * c->cw * 3 * sizeof(float);
+		if (off % 16 || bytes % 16) return set_err(KFB_E_STATE, "pixel-row band is not 16-byte aligned (%u columns)", c->cw);
+		BandPushParams bp;
+		bp.vertex = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(c->d_vertex) + off);
+		bp.normal = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(c->d_normal) + off);
+		bp.n_peer = 0;
+		for (int r = 0; r < c->world; ++r) if (r != c->rank) {
+			bp.peer_vertex[bp.n_peer] = reinterpret_cast<uint4*>(reinterpret_cast<char*>(c->peer_vertex[r]) + off);
+			bp.peer_normal[bp.n_peer] = reinterpret_cast<uint4*>(reinterpret_cast<char*>(c->peer_normal[r]) + off);
+			++bp.n_peer;
+		}
+		bp.n16 = (uint32_t) (bytes / 16);
+		if (bp.n16) { k_band_push<<<148, 256, 0, c->stream>>>(bp); LAUNCHED(c); }
+	}
 	CK(cudaGetLastError());
 	c->overlap_ok = c->overlap_enabled;   // until anything else is enqueued
 	return 0;
@@ -1258,8 +1287,7 @@ static int resolve_buffer(kfb_ctx* c, int which, int level, void** ptr, size_t* 
 		if (!c->brick.flag) return set_err(KFB_E_STATE, "brick flags are not maintained by this context");
 		*ptr = c->brick.flag; *bytes = (size_t) c->brick.bnx * c->brick.bny * c->brick.bnz; break;
 	case KFB_BUF_RAYTILECOST:
-		if (!c->d_tile_cost) return set_err(KFB_E_STATE, "tile costs are only recorded with KFB_RAY_TILECOST=1");
-		*ptr = c->d_tile_cost; *bytes = (size_t) ((c->cw + 7) / 8) * ((c->ch + 3) / 4) * sizeof(unsigned int); break;
+		*ptr = c->d_tile_cost; *bytes = (size_t) c->ray_tiles_cap * sizeof(unsigned int); break;
 	case KFB_BUF_BRICKCLASS: *ptr = c->d_cls; *bytes = c->cls_bytes; break;
 	default: return set_err(KFB_E_ARG, "unknown buffer %d", which);
 	}

@@ -1250,9 +1250,13 @@ __device__ __forceinline__ float3 vol_grad(const VolView& v, float3 pos) {  // c
 	return g * f3(v.dx / (float) v.sx, v.dy / (float) v.sy, v.dz / (float) v.sz) * (0.5f * 0.00003051944088f);
 }
 
+#ifndef RAY_STATS
+#define RAY_STATS 0   // development: KFB_BUF_RAYTILECOST holds, per tile, the max over its rays of 1 loop iterations,
+#endif                // 2 samples read from the volume, 3 leaps, 4 iterations in fine mode, 5 leapt steps — instead of cycles
+#define RAY_STAT(K) do { if (RAY_STATS == (K)) ++*stat; } while (0)
 // cpp/kernels.cpp:674-725; returns hit.xyz, *tw = hit.w
 __device__ __forceinline__ float3 raycast_one(const VolView& v, uint32_t px, uint32_t py, const Mat4& view, float nearPlane,
-		float farPlane, float step, float largestep, float* tw) {
+		float farPlane, float step, float largestep, float* tw, unsigned int* stat = nullptr) {
 	const float3 origin = f3(view.m[3], view.m[7], view.m[11]);
 	const float3 direction = mat_rotate(view, f3((float) px, (float) py, 1.f));
 	const float3 invR = f3(1.0f / direction.x, 1.0f / direction.y, 1.0f / direction.z);
@@ -1278,6 +1282,8 @@ __device__ __forceinline__ float3 raycast_one(const VolView& v, uint32_t px, uin
 			const bool leap = !v.no_leap;
 			for (; t < tfar; t += stepsize) {
 				const VolCell c = vol_cell(v, origin + direction * t);
+				RAY_STAT(1);
+				if (stepsize == step) RAY_STAT(4);
 				if (vol_cell_free(v, c)) {
 					f_tt = 1.f; lazy = true; t_lazy = t;
 					// Fine steps (one voxel each) inside a clear brick: the next samples whose base voxel provably stays in
@@ -1301,16 +1307,19 @@ __device__ __forceinline__ float3 raycast_one(const VolView& v, uint32_t px, uin
 							const float rz = (ds.z > 0.f ? hi - pz_ : pz_ - 0.05f) * rcp_approx(fabsf(ds.z) + 1e-20f);
 							const float room = kminf(kminf(rx, ry), rz);
 							int n = (room > 0.f) ? (int) kminf(room * rcp_approx(stepsize), 64.f) - 1 : 0;
+							if (n > 0) RAY_STAT(3);
 							while (n > 0) {
 								const float tn = t + stepsize;
 								if (!(tn < tfar)) break;   // the loop's own increment and test end the march
 								t = tn; t_lazy = tn; --n;
+								RAY_STAT(5);
 							}
 						}
 					}
 					continue;
 				}
 				f_tt = vol_interp_cell(v, c);
+				RAY_STAT(2);
 				if (f_tt < 0) break;
 				if (f_tt < 0.8f) stepsize = step;
 				f_t = f_tt;
@@ -1328,20 +1337,35 @@ __device__ __forceinline__ float3 raycast_one(const VolView& v, uint32_t px, uin
 	return f3(0, 0, 0);
 }
 
+// Slow tiles first.  The kernel ends when its slowest tile does, and a tile's cost hardly changes from one frame to the
+// next (the camera moves a little): every launch records the cycles each tile kept its warp, and lists the tiles above
+// 1.5 x the previous launch's mean for the NEXT launch, which hands those out before the rest in index order.  Which warp
+// computes which tile changes nothing in the maps.  Three rotating slots: read by this launch / appended to for the next /
+// zeroed for the one after.
+#ifndef RAY_SUBTILES
+#define RAY_SUBTILES 1   // a slow tile is handed out as this many 4x2-pixel parts (1: whole; 4 measured slower: a quarter's chain is as long as the tile's)
+#endif
+static_assert(RAY_SUBTILES == 1 || RAY_SUBTILES == 4, "k_raycast maps lanes to quarters");
+struct RaySched {
+	unsigned int* cost;                         // [tiles] cycles of the last launch (also KFB_BUF_RAYTILECOST)
+	unsigned int* stamp;                        // [tiles] launch number for which the tile is on the slow list
+	const unsigned int* slow_cur; unsigned int* slow_next;
+	const unsigned int* n_cur; unsigned int* n_next; unsigned int* n_zero;
+	const unsigned int* sum_cur; unsigned int* sum_next; unsigned int* sum_zero;   // sum of cost >> 6
+	unsigned int launch;                        // this launch's number (from 1)
+	int enabled;                                // 0 (KFB_RAY_NO_SCHED=1): index order, costs still recorded
+};
 struct RaycastParams {
-	unsigned int* tile_cost;        // optional: SM cycles each 8x4 tile took (KFB_RAY_TILECOST=1, diagnostics)
 	VolView vol;
 	float* vertex; float* normal;   // packed float3[w*h]
 	uint32_t w, h;
 	uint32_t row0, row1;            // rows handled by this context (multi-GPU: a band of pixels)
 	Mat4 view;
 	const float* view_dev;          // optional: the view matrix comes from the ICP kernel's tail (DevFrame::view)
-	// z-slab mode over peer memory: this rank's band of pixels is also stored into every peer's maps (the all-gather, fused)
-	float* peer_vertex[KFB_MAX_SLABS - 1]; float* peer_normal[KFB_MAX_SLABS - 1];
-	int n_peer;
 	float nearPlane, farPlane, step, largestep;
 	unsigned int* tile_next;        // dynamic tile counter of this launch; tile_reset is zeroed for the next one
 	unsigned int* tile_reset;
+	RaySched sched;
 };
 
 #define RC_BX 16
@@ -1361,18 +1385,40 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY, KFB_RAY_MINBLOCKS) k_raycast(R
 	if (threadIdx.x < 16) view.m[threadIdx.x] = p.view_dev ? __ldg(p.view_dev + threadIdx.x) : p.view.m[threadIdx.x];
 	__syncthreads();
 	const uint32_t tiles_x = (p.w + 7) / 8, tiles_y = (p.row1 - p.row0 + 3) / 4, tiles = tiles_x * tiles_y;
+	if (blockIdx.x == 0 && threadIdx.x == 0) { *p.sched.n_zero = 0u; *p.sched.sum_zero = 0u; }
+	const uint32_t n_slow = __ldcg(p.sched.n_cur), n_first = n_slow * RAY_SUBTILES;
+	const uint32_t mean = __ldcg(p.sched.sum_cur) / (tiles ? tiles : 1u);
+	const uint32_t slow_thr = (mean && p.sched.enabled) ? mean + (mean >> 1) : 0xffffffffu;
 	for (;;) {
 		uint32_t t = 0;
 		if (lane == 0) t = atomicAdd(p.tile_next, 1u);
 		t = __shfl_sync(0xffffffffu, t, 0);
-		if (t >= tiles) break;
+		bool mine = true;        // this lane's pixel belongs to the claim
+		bool part = false;       // the claim is a quarter of a slow tile
+		if (t < n_first) {
+			if (RAY_SUBTILES > 1) {
+				// a slow tile goes to RAY_SUBTILES warps, 4x2 pixels each: its rays diverge (some leap, some sample, a few
+				// walk hundreds of fine steps), and a warp pays for every path its lanes take
+				const uint32_t sub = t % RAY_SUBTILES;
+				t /= RAY_SUBTILES;
+				mine = (((lane & 7) >> 2) | ((lane >> 4) << 1)) == sub;
+				part = true;
+			}
+			t = __ldcg(p.sched.slow_cur + t);
+			if (t >= tiles) continue;                                  // the band shrank since the list was made
+		} else {
+			t -= n_first;
+			if (t >= tiles) break;
+			if (__ldcg(p.sched.stamp + t) == p.sched.launch) continue;   // handed out from the slow list
+		}
 		const uint32_t x = (t % tiles_x) * 8 + (lane & 7);
 		const uint32_t y = p.row0 + (t / tiles_x) * 4 + (lane >> 3);
-		const long long c0 = p.tile_cost ? clock64() : 0;
-		if (x < p.w && y < p.row1) {
+		const long long c0 = clock64();
+		unsigned int stat = 0;
+		if (mine && x < p.w && y < p.row1) {
 			const size_t idx = (size_t) x + (size_t) y * p.w;
 			float hw;
-			const float3 hit = raycast_one(p.vol, x, y, view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw);
+			const float3 hit = raycast_one(p.vol, x, y, view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw, &stat);
 			if (hw > 0.0f) {
 				st3(p.vertex, idx, hit);
 				const float3 surfNorm = vol_grad(p.vol, hit);
@@ -1382,16 +1428,16 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY, KFB_RAY_MINBLOCKS) k_raycast(R
 				st3(p.vertex, idx, f3(0, 0, 0));
 				st3(p.normal, idx, f3(KFB_INVALID, 0, 0));
 			}
-			if (p.n_peer) {
-				// z-slab group: the pixel as it now stands in this rank's maps (including the components an x-only normal write
-				// left from the previous frame: the owner of a pixel never changes) goes to every peer
-				const float3 vv = ld3(p.vertex, idx), nn = ld3(p.normal, idx);
-				for (int i = 0; i < p.n_peer; ++i) { st3(p.peer_vertex[i], idx, vv); st3(p.peer_normal[i], idx, nn); }
-			}
 		}
-		if (p.tile_cost) {   // diagnostics (KFB_RAY_TILECOST=1): how long this tile kept its warp
-			__syncwarp();
-			if (lane == 0) p.tile_cost[t] = (unsigned int) (clock64() - c0);
+		__syncwarp();
+		if (RAY_STATS) stat = __reduce_max_sync(0xffffffffu, stat);
+		if (lane == 0) {   // how long this claim kept its warp: the next launch's schedule (and KFB_BUF_RAYTILECOST)
+			const unsigned int cost = (unsigned int) (clock64() - c0), cs = cost >> 6;
+			p.sched.cost[t] = RAY_STATS ? stat : cost;   // (of a tile handed out in quarters: one quarter's)
+			atomicAdd(p.sched.sum_next, cs);
+			// a quarter stays on the list while its own chain is long
+			if (cs > (part ? slow_thr / 3 : slow_thr) && atomicExch(p.sched.stamp + t, p.sched.launch + 1u) != p.sched.launch + 1u)
+				p.sched.slow_next[atomicAdd(p.sched.n_next, 1u)] = t;   // < tiles entries: a tile is listed once
 		}
 	}
 }
@@ -1468,6 +1514,28 @@ __global__ void __launch_bounds__(RC_BX* RC_BY) k_render_volume(RenderVolumePara
 		}
 	}
 	p.out[(size_t) x + (size_t) y * p.w] = o;
+}
+
+// ------------------------------------------------------------------------------------------
+// z-slab group: this rank's band of the raycast maps (rows [row0, row1): contiguous in memory) goes to every peer's maps —
+// the all-gather, as coalesced 16-byte stores over NVLink right behind k_raycast.  (Storing each pixel to the peers from
+// inside k_raycast — 1.6 M scattered 4-byte remote writes per rank and frame — measured the same on 8 GPUs, 1329 vs 1309
+// fps at 1024^3: the stage is bound by the rays' voxel reads from peer slabs, not by the exchange.  This form keeps
+// k_raycast free of peer pointers.)  The band as it stands in this rank's maps is copied, including the components an x-only normal write left
+// from the previous frame: the owner of a pixel never changes, so every rank's maps stay bit-identical to the owner's.
+// ------------------------------------------------------------------------------------------
+struct BandPushParams {
+	const uint4* vertex; const uint4* normal;   // this rank's band (first byte of row0)
+	uint4* peer_vertex[KFB_MAX_SLABS - 1]; uint4* peer_normal[KFB_MAX_SLABS - 1];
+	int n_peer;
+	uint32_t n16;                               // 16-byte words per map band
+};
+__global__ void __launch_bounds__(256) k_band_push(BandPushParams p) {
+	const uint32_t stride = gridDim.x * blockDim.x;
+	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < p.n16; i += stride) {
+		const uint4 v = __ldcg(p.vertex + i), n = __ldcg(p.normal + i);
+		for (int r = 0; r < p.n_peer; ++r) { p.peer_vertex[r][i] = v; p.peer_normal[r][i] = n; }
+	}
 }
 
 // ------------------------------------------------------------------------------------------

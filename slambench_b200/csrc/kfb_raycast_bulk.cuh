@@ -139,10 +139,6 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY, 8) k_raycast_bulk(RaycastParam
 					else st3(p.normal, idx, knormalize(surfNorm));
 				} else { st3(p.vertex, idx, f3(0, 0, 0)); st3(p.normal, idx, f3(KFB_INVALID, 0, 0)); }
 			} else { st3(p.vertex, idx, f3(0, 0, 0)); st3(p.normal, idx, f3(KFB_INVALID, 0, 0)); }
-			if (p.n_peer) {   // z-slab group: the pixel as it stands in this rank's maps goes to every peer (see k_raycast)
-				const float3 vv = ld3(p.vertex, idx), nn = ld3(p.normal, idx);
-				for (int i = 0; i < p.n_peer; ++i) { st3(p.peer_vertex[i], idx, vv); st3(p.peer_normal[i], idx, nn); }
-			}
 		}
 	}
 	if (bulk_stats) {

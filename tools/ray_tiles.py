@@ -1,6 +1,5 @@
-"""Distribution of the raycaster's per-tile cost (SM cycles per 8x4-pixel tile): KFB_RAY_TILECOST=1 python tools/ray_tiles.py [volume] [frames]"""
+"""Distribution of the raycaster's per-tile cost (SM cycles per 8x4-pixel tile): python tools/ray_tiles.py [volume] [frames]   (RAY_TILES_OUT=<file.npy> keeps the array)"""
 import os, sys
-os.environ.setdefault("KFB_RAY_TILECOST", "1")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import numpy as np
@@ -16,7 +15,8 @@ with kf.Kfusion((640, 480), vres, 4.8, T0, (10, 5, 4)) as g:
         g.preprocessing(depth[f]); g.tracking(K, 1e-5, 1, f); g.integration(K, 1, 0.1, f); g.raycasting(K, 0.1, f)
     g.synchroniseDevices()
     c = g.read(kf.BUF_RAYTILECOST).astype(np.float64)
-    warps = 148 * 32
+    if os.environ.get("RAY_TILES_OUT"): np.save(os.environ["RAY_TILES_OUT"], c)
+    warps = 148 * 36
     print(f"{vres}^3 frame {frames - 1}: tiles {c.size}, sum {c.sum() / 1e6:.1f} Mcycles = {c.sum() / warps / 1.965e3:.1f} us per warp slot at 1.965 GHz")
     print("percentiles (kcycles): " + ", ".join(f"p{q}={np.percentile(c, q) / 1e3:.1f}" for q in (50, 90, 99, 99.9, 100)))
     rows = c.max(axis=1)
