@@ -20,8 +20,11 @@ SURVEY §8a a18), so every timed frame is tracked + integrated + raycast.
             built, the plain-C restatement, timed on this box's host cores on a bounded sample
 
 N > 1: one process per GPU, one independent sequence per GPU (BASELINE configs[2]), no data-path
-collective; value = sum of frames / max-over-ranks time ("weak" scaling).  `--mode sharded` instead
-runs ONE sequence on a volume cut into z-slabs over the ranks (configs[3], [4]; "strong" scaling).
+collective; value = sum of frames / max-over-ranks time ("weak" scaling).  The same line then carries
+a "sharded" key: ONE sequence on ONE volume cut into z-slabs over the ranks (configs[3] 1024^3, and
+configs[4] 2048^3 from 8 GPUs on), moved over NVLink peer memory by the library itself, with the slab
+cut picked at set-up by timing a few candidate partitions (`--no-slab-tuning`, `--no-sharded`,
+`--sharded-steps`).  `--mode sharded --volume V` prints that run as a line of its own ("strong" scaling).
 """
 from __future__ import annotations
 

@@ -112,6 +112,23 @@ def test_preprocess_invalid_ratio_is_an_error():
             g.preprocessing(np.zeros((100, 100), np.uint16))
 
 
+def test_create_rejects_bad_slabs_and_frees_the_context():
+    """A z-slab starts on a brick layer (the brick flags and the integrate items assume it), lies inside the volume, and a
+    failed create leaves nothing behind: many failures in a row must not leak device memory."""
+    import torch
+    with pytest.raises(kf.KfbError, match="multiple of 8"):
+        kf.Kfusion((640, 480), 64, 4.8, T0, (10, 5, 4), slab=(4, 64))
+    with pytest.raises(kf.KfbError, match="bad z-slab"):
+        kf.Kfusion((640, 480), 64, 4.8, T0, (10, 5, 4), slab=(8, 72))
+    free0 = torch.cuda.mem_get_info(0)[0]
+    for _ in range(20):
+        with pytest.raises(kf.KfbError):
+            kf.Kfusion((640, 480), 256, 4.8, T0, (10, 5, 4), slab=(4, 256))
+    assert free0 - torch.cuda.mem_get_info(0)[0] < (8 << 20), "failed creates leak device memory"
+    with kf.Kfusion((640, 480), 64, 4.8, T0, (10, 5, 4), slab=(8, 56)) as g:   # an aligned inner slab is fine
+        g.synchroniseDevices()
+
+
 def test_pyramid_vertex_normal_bit_exact(port, gpu, state):
     gpu.write(kf.BUF_SCALEDDEPTH, state["sd"][0], 0)
     gpu.pyramidKernels(K)
