@@ -1519,9 +1519,9 @@ __global__ void __launch_bounds__(RC_BX* RC_BY) k_render_volume(RenderVolumePara
 // ------------------------------------------------------------------------------------------
 // z-slab group: this rank's band of the raycast maps (rows [row0, row1): contiguous in memory) goes to every peer's maps —
 // the all-gather, as coalesced 16-byte stores over NVLink right behind k_raycast.  (Storing each pixel to the peers from
-// inside k_raycast — 1.6 M scattered 4-byte remote writes per rank and frame — measured the same on 8 GPUs, 1329 vs 1309
-// fps at 1024^3: the stage is bound by the rays' voxel reads from peer slabs, not by the exchange.  This form keeps
-// k_raycast free of peer pointers.)  The band as it stands in this rank's maps is copied, including the components an x-only normal write left
+// inside k_raycast — 1.6 M scattered 4-byte remote writes per rank and frame — measured within 3 % on 8 GPUs, 1329 vs
+// 1287 - 1309 fps at 1024^3: the stage is bound by the rays' voxel reads from peer slabs, not by the exchange.  This form
+// keeps k_raycast free of peer pointers.)  The band as it stands in this rank's maps is copied, including the components an x-only normal write left
 // from the previous frame: the owner of a pixel never changes, so every rank's maps stay bit-identical to the owner's.
 // ------------------------------------------------------------------------------------------
 struct BandPushParams {
