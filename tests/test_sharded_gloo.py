@@ -37,7 +37,18 @@ def test_partitions():
         assert all(a[1] == b[0] for a, b in zip(sl, sl[1:])) and all(z0 % 8 == 0 and z1 > z0 for z0, z1 in sl)
         assert sl[0][1] - sl[0][0] > sl[-1][1] - sl[-1][0]
     assert sharded.slab_bounds(64, 4, np.ones(64), align=8)[0][0] == 0
+    # worlds that do not divide the volume (256^3 on 3 ranks used to start slabs at z = 86, 171): every
+    # partition the sharded host can choose starts its slabs on brick layers, which kfb_create also insists on
     from slambench_b200 import synth
+    Kc = np.array(synth.K_DEFAULT, np.float32)
+    pose = kf.identity_pose(np.array(synth.INIT_POS_FACTOR, np.float32) * np.float32(4.8))
+    for n_z, world in ((256, 3), (256, 5), (256, 7), (1024, 6), (100, 3)):
+        parts = dict(sharded.candidate_slabs(n_z, world, 4.8, pose, Kc, (640, 480), far=4.0))
+        parts["default"] = sharded.slab_bounds(n_z, world, align=8)
+        for name, sl in parts.items():
+            assert len(sl) == world and sl[0][0] == 0 and sl[-1][1] == n_z, (name, sl)
+            assert all(a[1] == b[0] for a, b in zip(sl, sl[1:])), (name, sl)
+            assert all(z0 % 8 == 0 and z1 > z0 for z0, z1 in sl), (name, sl)
     K = np.array(synth.K_DEFAULT, np.float32)
     fw = sharded.frustum_slice_weights(64, 4.8, kf.identity_pose([2.4, 2.4, 1.2]), K, (640, 480), far=3.2)
     assert fw[:16].sum() == 0 and fw[20:56].min() > 0 and np.all(np.diff(fw[20:56]) >= 0)    # behind the camera: nothing; then growing
