@@ -54,6 +54,47 @@ def test_drop_in_benchmark_matches_reference_binary(tmp_path):
     assert a[4:, 7].mean() < b[4:, 7].mean() / 20
 
 
+OMP_BIN = os.path.join(ROOT, "oracle", "_ref", "kfusion-benchmark-openmp")
+
+
+@pytest.mark.slow
+@pytest.mark.skipif(not (os.path.exists(B200_BIN) and os.path.exists(OMP_BIN)), reason="benchmark binaries not built (need /root/reference at build time)")
+def test_baseline_config_100_frames_512_free_running(tmp_path):
+    """BASELINE configs[1] itself inside pytest: 100 frames, 512^3, 4.8 m, mu 0.1, pyramid 10,5,4, every frame tracked and
+    integrated, FREE-RUNNING (each backend tracks against its own model) — the drop-in binary next to the reference's own
+    OpenMP binary (the unmodified kernels.cpp; the single-thread -cpp build takes 0.6 s per frame at this size).  Gates:
+    identical tracked / integrated columns over all 100 frames, logged position within north_star's 1e-4 m at EVERY frame,
+    and the final 512^3 volume dump within 1 LSB on > 99.5 % of its 134 M voxels (poses that differ in the 7th digit move
+    a few band voxels by more)."""
+    n, vres = 100, 512
+    depth, _ = synth.make_sequence(n)
+    raw = str(tmp_path / "seq.raw")
+    synth.write_raw(raw, depth)
+    logs, dumps = {}, {}
+    for name, exe in (("b200", B200_BIN), ("omp", OMP_BIN)):
+        log, dump = str(tmp_path / f"{name}.log"), str(tmp_path / f"{name}.vol")
+        cmd = [exe, "-i", raw, "-s", "4.8", "-p", "0.5,0.5,0.25", "-z", "1000", "-c", "1", "-r", "1", "-t", "1", "-m", "0.1", "-y", "10,5,4",
+               "-l", "1e-5", "-k", "481.2,480,320,240", "-v", str(vres), "-o", log, "-d", dump]
+        subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, timeout=900)
+        logs[name] = parse_log(log)
+        dumps[name] = np.fromfile(dump, dtype=np.int16)
+        os.remove(dump)
+    a, b = logs["b200"], logs["omp"]
+    assert a.shape == b.shape == (n, 14)
+    assert np.array_equal(a[:, 12:], b[:, 12:]), "tracked / integrated columns differ"
+    assert list(b[:, 12]) == [0] * 4 + [1] * (n - 4), "the reference must track every frame of this sequence"
+    err = np.abs(a[:, 9:12] - b[:, 9:12]).max(axis=1)
+    assert err.max() <= 1e-4, f"logged X,Y,Z differ by {err.max():.2e} m at frame {int(err.argmax())}"
+    assert dumps["b200"].size == dumps["omp"].size == vres ** 3
+    close, same, CH = 0, 0, 1 << 24
+    for i in range(0, vres ** 3, CH):   # in chunks: the int32 difference of 134 M voxels at once is 1 GB
+        d = np.abs(dumps["b200"][i:i + CH].astype(np.int32) - dumps["omp"][i:i + CH].astype(np.int32))
+        close += int((d <= 1).sum()); same += int((d == 0).sum())
+    print(f"512^3 after {n} free-running frames: max position difference {err.max():.2e} m, tsdf identical on {same / vres ** 3:.6f}, within 1 LSB on {close / vres ** 3:.6f}")
+    assert close / vres ** 3 > 0.995
+    assert a[4:, 7].mean() < b[4:, 7].mean() / 10, "computation column: the drop-in is supposed to be fast"
+
+
 @pytest.mark.skipif(not os.path.exists(B200_BIN), reason="benchmark binary not built (needs /root/reference at build time)")
 def test_drop_in_benchmark_z_slab_group(tmp_path):
     """configs[3] from the C++ host: two processes of the SAME drop-in binary (KFB_WORLD / KFB_RANK / KFB_RDV, one GPU each;
