@@ -192,7 +192,8 @@ int kfb_slab_import(kfb_ctx* ctx, int rank, int world, const uint8_t* handles64,
 /* The same over PEER MEMORY only (no NCCL on the data path): besides its slab, every context exports its raycast maps, its
  * brick-flag map and a barrier slot.  After kfb_ipc_import a context
  *   - stores the brick flags of its slab into every peer's map while it integrates (nothing to merge afterwards),
- *   - stores its band of the raycast vertex / normal maps into every peer's maps (the all-gather, fused into k_raycast),
+ *   - copies its band of the raycast vertex / normal maps into every peer's maps right behind k_raycast (the all-gather, as one
+ *     kernel of 16-byte stores over NVLink; the band — whole rows — must start and end on 16 bytes: width * 12 % 16 == 0),
  *   - ends kfb_integrate and kfb_raycast with a stream-ordered barrier over the group (kfb_peer_barrier),
  * so a host only has to move the 64-byte handles between its processes once (files, pipes, MPI, torch.distributed ...)
  * and then drives every rank with the ordinary stage calls.  All ranks must issue the same calls in the same order. */
