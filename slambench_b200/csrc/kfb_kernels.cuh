@@ -1341,11 +1341,8 @@ __device__ __forceinline__ float3 raycast_one(const VolView& v, uint32_t px, uin
 // next (the camera moves a little): every launch records the cycles each tile kept its warp, and lists the tiles above
 // 1.5 x the previous launch's mean for the NEXT launch, which hands those out before the rest in index order.  Which warp
 // computes which tile changes nothing in the maps.  Three rotating slots: read by this launch / appended to for the next /
-// zeroed for the one after.
-#ifndef RAY_SUBTILES
-#define RAY_SUBTILES 1   // a slow tile is handed out as this many 4x2-pixel parts (1: whole; 4 measured slower: a quarter's chain is as long as the tile's)
-#endif
-static_assert(RAY_SUBTILES == 1 || RAY_SUBTILES == 4, "k_raycast maps lanes to quarters");
+// zeroed for the one after.  (Handing a slow tile out as four 4x2-pixel quarters to four warps was measured slower: a
+// quarter's chain is as long as the tile's — profiles/r2_summary.md.)
 struct RaySched {
 	unsigned int* cost;                         // [tiles] cycles of the last launch (also KFB_BUF_RAYTILECOST)
 	unsigned int* stamp;                        // [tiles] launch number for which the tile is on the slow list
@@ -1386,28 +1383,18 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY, KFB_RAY_MINBLOCKS) k_raycast(R
 	__syncthreads();
 	const uint32_t tiles_x = (p.w + 7) / 8, tiles_y = (p.row1 - p.row0 + 3) / 4, tiles = tiles_x * tiles_y;
 	if (blockIdx.x == 0 && threadIdx.x == 0) { *p.sched.n_zero = 0u; *p.sched.sum_zero = 0u; }
-	const uint32_t n_slow = __ldcg(p.sched.n_cur), n_first = n_slow * RAY_SUBTILES;
+	const uint32_t n_slow = __ldcg(p.sched.n_cur);
 	const uint32_t mean = __ldcg(p.sched.sum_cur) / (tiles ? tiles : 1u);
 	const uint32_t slow_thr = (mean && p.sched.enabled) ? mean + (mean >> 1) : 0xffffffffu;
 	for (;;) {
 		uint32_t t = 0;
 		if (lane == 0) t = atomicAdd(p.tile_next, 1u);
 		t = __shfl_sync(0xffffffffu, t, 0);
-		bool mine = true;        // this lane's pixel belongs to the claim
-		bool part = false;       // the claim is a quarter of a slow tile
-		if (t < n_first) {
-			if (RAY_SUBTILES > 1) {
-				// a slow tile goes to RAY_SUBTILES warps, 4x2 pixels each: its rays diverge (some leap, some sample, a few
-				// walk hundreds of fine steps), and a warp pays for every path its lanes take
-				const uint32_t sub = t % RAY_SUBTILES;
-				t /= RAY_SUBTILES;
-				mine = (((lane & 7) >> 2) | ((lane >> 4) << 1)) == sub;
-				part = true;
-			}
+		if (t < n_slow) {
 			t = __ldcg(p.sched.slow_cur + t);
 			if (t >= tiles) continue;                                  // the band shrank since the list was made
 		} else {
-			t -= n_first;
+			t -= n_slow;
 			if (t >= tiles) break;
 			if (__ldcg(p.sched.stamp + t) == p.sched.launch) continue;   // handed out from the slow list
 		}
@@ -1415,7 +1402,7 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY, KFB_RAY_MINBLOCKS) k_raycast(R
 		const uint32_t y = p.row0 + (t / tiles_x) * 4 + (lane >> 3);
 		const long long c0 = clock64();
 		unsigned int stat = 0;
-		if (mine && x < p.w && y < p.row1) {
+		if (x < p.w && y < p.row1) {
 			const size_t idx = (size_t) x + (size_t) y * p.w;
 			float hw;
 			const float3 hit = raycast_one(p.vol, x, y, view, p.nearPlane, p.farPlane, p.step, p.largestep, &hw, &stat);
@@ -1431,13 +1418,14 @@ __global__ void __launch_bounds__(RCK_BX* RCK_BY, KFB_RAY_MINBLOCKS) k_raycast(R
 		}
 		__syncwarp();
 		if (RAY_STATS) stat = __reduce_max_sync(0xffffffffu, stat);
-		if (lane == 0) {   // how long this claim kept its warp: the next launch's schedule (and KFB_BUF_RAYTILECOST)
+		if (lane == 0) {   // how long this tile kept its warp: the next launch's schedule (and KFB_BUF_RAYTILECOST)
 			const unsigned int cost = (unsigned int) (clock64() - c0), cs = cost >> 6;
-			p.sched.cost[t] = RAY_STATS ? stat : cost;   // (of a tile handed out in quarters: one quarter's)
+			p.sched.cost[t] = RAY_STATS ? stat : cost;
 			atomicAdd(p.sched.sum_next, cs);
-			// a quarter stays on the list while its own chain is long
-			if (cs > (part ? slow_thr / 3 : slow_thr) && atomicExch(p.sched.stamp + t, p.sched.launch + 1u) != p.sched.launch + 1u)
-				p.sched.slow_next[atomicAdd(p.sched.n_next, 1u)] = t;   // < tiles entries: a tile is listed once
+			if (cs > slow_thr) {
+				p.sched.slow_next[atomicAdd(p.sched.n_next, 1u)] = t;   // <= tiles entries: a tile is computed once per launch
+				p.sched.stamp[t] = p.sched.launch + 1u;
+			}
 		}
 	}
 }
